@@ -1,0 +1,128 @@
+"""ctypes binding of the C ABI (include/capital_b200.h).  The shared library is built in-tree by
+capital_b200/build.py; there is no fallback implementation: a missing library or device is an error."""
+from __future__ import annotations
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcapital_b200.so")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_NOT_SPD, ERR_COMM, ERR_UNSUPPORTED = range(6)
+RECT, UPPERTRI_PACKED = 0, 1
+GEMM_A_UPPER, GEMM_A_LOWER, GEMM_B_UPPER, GEMM_B_LOWER, GEMM_C_UPPER = 1, 2, 4, 8, 16
+
+EXPORTS = [  # every symbol include/capital_b200.h declares
+    "capital_grid_square", "capital_grid_rect", "capital_cholinv_bc_dimension", "capital_create",
+    "capital_comm_unique_id", "capital_comm_init", "capital_destroy", "capital_last_error", "capital_get_counters",
+    "capital_reset_counters", "capital_synchronize", "capital_last_factor_ms", "capital_distribute_symmetric_f64",
+    "capital_distribute_random_f64", "capital_cholinv_factor_f64", "capital_cholinv_residual_f64",
+    "capital_cacqr_factor_f64", "capital_cacqr_residual_f64", "capital_blas_gemm_tn_f64",
+    "capital_lapack_potrf_trtri_f64",
+]
+
+
+class Grid(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("size", "rank", "c", "d", "x", "y", "z", "layout", "num_chunks")]
+
+
+class CholinvArgs(C.Structure):
+    _fields_ = [("complete_inv", C.c_int64), ("split", C.c_int64), ("bc_mult_dim", C.c_int64), ("dir", C.c_char)]
+
+
+class Counters(C.Structure):
+    _fields_ = [("kernel_launches", C.c_int64), ("gemm_launches", C.c_int64), ("leaf_launches", C.c_int64),
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("gemm_flops", C.c_double)]
+
+
+class CapitalError(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"capital_b200 status {status}: {msg}")
+        self.status = status
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python -m capital_b200.build` (there is no fallback path)")
+    L = C.CDLL(LIB_PATH)
+    vp, i64, dbl, ci = C.c_void_p, C.c_int64, C.c_double, C.c_int
+    L.capital_grid_square.argtypes = [ci, ci, ci, ci, ci, C.POINTER(Grid)]
+    L.capital_grid_rect.argtypes = [ci, ci, ci, ci, ci, C.POINTER(Grid)]
+    L.capital_cholinv_bc_dimension.argtypes = [i64, ci, ci, i64]
+    L.capital_cholinv_bc_dimension.restype = i64
+    L.capital_create.argtypes = [C.POINTER(vp), C.POINTER(Grid), ci, vp]
+    L.capital_comm_unique_id.argtypes = [vp]
+    L.capital_comm_init.argtypes = [vp, vp]
+    L.capital_destroy.argtypes = [vp]
+    L.capital_destroy.restype = None
+    L.capital_last_error.argtypes = [vp]
+    L.capital_last_error.restype = C.c_char_p
+    L.capital_get_counters.argtypes = [vp, C.POINTER(Counters)]
+    L.capital_reset_counters.argtypes = [vp]
+    L.capital_synchronize.argtypes = [vp]
+    L.capital_last_factor_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.capital_distribute_symmetric_f64.argtypes = [vp, vp, i64, ci]
+    L.capital_distribute_random_f64.argtypes = [vp, vp, i64, i64, i64]
+    L.capital_cholinv_factor_f64.argtypes = [vp, vp, i64, C.POINTER(CholinvArgs), ci, vp, vp]
+    L.capital_cholinv_residual_f64.argtypes = [vp, vp, i64, ci, vp, C.POINTER(dbl)]
+    L.capital_cacqr_factor_f64.argtypes = [vp, vp, i64, i64, ci, C.POINTER(CholinvArgs), ci, vp, vp]
+    L.capital_cacqr_residual_f64.argtypes = [vp, vp, i64, i64, vp, ci, vp, C.POINTER(dbl), C.POINTER(dbl)]
+    L.capital_blas_gemm_tn_f64.argtypes = [vp, i64, i64, i64, dbl, vp, i64, vp, i64, dbl, vp, i64, ci]
+    L.capital_lapack_potrf_trtri_f64.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64]
+    for name in EXPORTS:
+        fn = getattr(L, name)
+        if name not in ("capital_destroy", "capital_last_error", "capital_cholinv_bc_dimension"):
+            fn.restype = ci
+    _lib = L
+    return L
+
+
+class Context:
+    """One context per process / GPU (capital_create ... capital_destroy)."""
+
+    def __init__(self, grid: Grid, device: int = 0, stream: int | None = None):
+        self.grid = grid
+        self._h = C.c_void_p()
+        st = lib().capital_create(C.byref(self._h), C.byref(grid), device, C.c_void_p(stream or 0))
+        if st != OK:
+            raise CapitalError(st, "capital_create failed (needs an sm_100 device; no CPU fallback exists)")
+
+    def check(self, status: int):
+        if status != OK:
+            raise CapitalError(status, lib().capital_last_error(self._h).decode())
+
+    @property
+    def handle(self):
+        return self._h
+
+    def counters(self) -> Counters:
+        c = Counters()
+        self.check(lib().capital_get_counters(self._h, C.byref(c)))
+        return c
+
+    def reset_counters(self):
+        self.check(lib().capital_reset_counters(self._h))
+
+    def synchronize(self):
+        self.check(lib().capital_synchronize(self._h))
+
+    def last_factor_ms(self) -> float:
+        ms = C.c_float()
+        self.check(lib().capital_last_factor_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def close(self):
+        if self._h:
+            lib().capital_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

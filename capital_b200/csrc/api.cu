@@ -1,0 +1,328 @@
+// C ABI (include/capital_b200.h): context, grid helpers, generators, validators and the factor entry points.
+// Host orchestration only -- every flop and every byte of layout work runs in the kernels of gemm_tn.cu,
+// leaf.cu and layout.cu.  There is no CPU fallback: without a usable sm_100 device capital_create fails.
+#include "common.cuh"
+#include "dist.cuh"
+#include <math.h>
+
+capital_status_t capital_ctx::workspace(const std::string& name, size_t bytes, void** out) {
+  capital_ctx* ctx = this;
+  DeviceBuf& b = pool[name];
+  if (b.bytes < bytes) {
+    if (b.p) CAP_CUDA(cudaFree(b.p));
+    b.p = nullptr; b.bytes = 0;
+    CAP_CUDA(cudaMalloc(&b.p, bytes));
+    b.bytes = bytes;
+  }
+  *out = b.p;
+  return CAPITAL_OK;
+}
+
+bool cap_is_device_ptr(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// Bring `count` doubles to the device (no-op for device pointers).
+capital_status_t cap_stage_in(capital_ctx* ctx, const double* src, size_t count, const char* name, const double** out) {
+  if (cap_is_device_ptr(src)) { *out = src; return CAPITAL_OK; }
+  void* d;
+  CAP_TRY(ctx->workspace(name, count * 8, &d));
+  CAP_CUDA(cudaMemcpyAsync(d, src, count * 8, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->counters.h2d_bytes += (int64_t)count * 8;
+  *out = (const double*)d;
+  return CAPITAL_OK;
+}
+// Device output target for a caller pointer: the pointer itself if on device, else a workspace to be copied back.
+capital_status_t cap_stage_out_begin(capital_ctx* ctx, double* dst, size_t count, const char* name, double** dev) {
+  if (cap_is_device_ptr(dst)) { *dev = dst; return CAPITAL_OK; }
+  void* d;
+  CAP_TRY(ctx->workspace(name, count * 8, &d));
+  *dev = (double*)d;
+  return CAPITAL_OK;
+}
+capital_status_t cap_stage_out_end(capital_ctx* ctx, double* dst, size_t count, const double* dev) {
+  if (dev == dst) return CAPITAL_OK;
+  CAP_CUDA(cudaMemcpyAsync(dst, dev, count * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->counters.d2h_bytes += (int64_t)count * 8;
+  return CAPITAL_OK;
+}
+
+capital_status_t cap_check_info(capital_ctx* ctx) {
+  int info = 0;
+  CAP_CUDA(cudaMemcpyAsync(&info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CAP_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (info != 0) {
+    ctx->set_error("matrix is not positive definite: non-positive pivot " + std::to_string(info) + " in a base-case block");
+    return CAPITAL_ERR_NOT_SPD;
+  }
+  return CAPITAL_OK;
+}
+
+extern "C" {
+
+capital_status_t capital_grid_square(int size, int rank, int c, int layout, int num_chunks, capital_grid_t* out) {
+  if (!out || size <= 0 || rank < 0 || rank >= size || c <= 0 || layout != 0) return CAPITAL_ERR_INVALID;
+  capital_grid_t g{};
+  g.size = size; g.rank = rank; g.c = c; g.layout = layout; g.num_chunks = num_chunks;
+  g.d = (int)nearbyint(ceil(sqrt((double)(size / c))));  // topology.h:77
+  g.z = rank % c;
+  g.y = rank / (g.d * c);
+  g.x = (rank % (g.d * c)) / c;
+  if ((int64_t)g.c * g.d * g.d != size) return CAPITAL_ERR_INVALID;
+  *out = g;
+  return CAPITAL_OK;
+}
+capital_status_t capital_grid_rect(int size, int rank, int c, int layout, int num_chunks, capital_grid_t* out) {
+  if (!out || size <= 0 || rank < 0 || rank >= size || c <= 0 || layout != 0) return CAPITAL_ERR_INVALID;
+  if (size % (c * c)) return CAPITAL_ERR_INVALID;
+  capital_grid_t g{};
+  g.size = size; g.rank = rank; g.c = c; g.layout = layout; g.num_chunks = num_chunks;
+  g.d = size / (c * c);  // topology.h:46
+  g.z = rank % c;
+  g.y = rank / (c * c);
+  g.x = (rank % (c * c)) / c;
+  *out = g;
+  return CAPITAL_OK;
+}
+int64_t capital_cholinv_bc_dimension(int64_t local_dim, int c, int d, int64_t bc_mult_dim) {
+  int64_t bc = (int64_t)c * d;  // cholinv.hpp:15-18
+  if (bc_mult_dim < 0) { for (int64_t i = 0; i < -bc_mult_dim; i++) bc *= 2; }
+  else { for (int64_t i = 0; i < bc_mult_dim; i++) bc /= 2; }
+  if (bc < 1) bc = 1;
+  if (bc > local_dim) bc = local_dim;
+  return (int64_t)d * (local_dim / bc);
+}
+
+capital_status_t capital_create(capital_ctx** out, const capital_grid_t* grid, int device, void* stream) {
+  if (!out || !grid) return CAPITAL_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return CAPITAL_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return CAPITAL_ERR_CUDA;
+  if (prop.major != 10) return CAPITAL_ERR_CUDA;  // sm_100a binary only: no fallback path exists
+  if (cudaSetDevice(device) != cudaSuccess) return CAPITAL_ERR_CUDA;
+  capital_ctx* ctx = new capital_ctx();
+  ctx->grid = *grid;
+  ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
+  if (stream) { ctx->stream = (cudaStream_t)stream; ctx->own_stream = false; }
+  else {
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return CAPITAL_ERR_CUDA; }
+    ctx->own_stream = true;
+  }
+  bool ok = cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaEventCreate(&ctx->ev_start) == cudaSuccess && cudaEventCreate(&ctx->ev_stop) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaMalloc(&ctx->d_info, sizeof(int)) == cudaSuccess && cudaMalloc(&ctx->d_scalars, 16 * sizeof(double)) == cudaSuccess;
+  ok = ok && cudaMemset(ctx->d_info, 0, sizeof(int)) == cudaSuccess;
+  cudaDriverEntryPointQueryResult qres;
+  void* fn = nullptr;
+  ok = ok && cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn != nullptr;
+  if (!ok) { capital_destroy(ctx); return CAPITAL_ERR_CUDA; }
+  ctx->encode = (cuTensorMapEncodeTiled_fn)fn;
+  *out = ctx;
+  return CAPITAL_OK;
+}
+
+void capital_destroy(capital_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  dist_destroy(ctx);
+  for (auto& kv : ctx->pool) if (kv.second.p) cudaFree(kv.second.p);
+  if (ctx->d_info) cudaFree(ctx->d_info);
+  if (ctx->d_scalars) cudaFree(ctx->d_scalars);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+  if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->side) cudaStreamDestroy(ctx->side);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* capital_last_error(const capital_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+capital_status_t capital_get_counters(const capital_ctx* ctx, capital_counters_t* out) {
+  if (!ctx || !out) return CAPITAL_ERR_INVALID;
+  *out = ctx->counters;
+  return CAPITAL_OK;
+}
+capital_status_t capital_reset_counters(capital_ctx* ctx) {
+  if (!ctx) return CAPITAL_ERR_INVALID;
+  ctx->counters = capital_counters_t{};
+  return CAPITAL_OK;
+}
+capital_status_t capital_synchronize(capital_ctx* ctx) {
+  if (!ctx) return CAPITAL_ERR_INVALID;
+  CAP_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CAPITAL_OK;
+}
+capital_status_t capital_last_factor_ms(const capital_ctx* ctx_, float* ms) {
+  capital_ctx* ctx = const_cast<capital_ctx*>(ctx_);
+  if (!ctx || !ms) return CAPITAL_ERR_INVALID;
+  CAP_CUDA(cudaEventElapsedTime(ms, ctx->ev_start, ctx->ev_stop));
+  return CAPITAL_OK;
+}
+
+// ---- generators -------------------------------------------------------------------------------
+capital_status_t capital_distribute_symmetric_f64(capital_ctx* ctx, double* A_local, int64_t n, int diag_dom) {
+  if (!ctx || !A_local || n <= 0) return CAPITAL_ERR_INVALID;
+  CAP_CUDA(cudaSetDevice(ctx->device));
+  const int d = ctx->grid.d;
+  const int64_t L = ceil_div(n, d);
+  double* dev;
+  CAP_TRY(cap_stage_out_begin(ctx, A_local, (size_t)L * L, "gen_out", &dev));
+  CAP_TRY(gen_symmetric(ctx, ctx->stream, dev, L, L, L, n, ctx->grid.x, ctx->grid.y, d, diag_dom));
+  CAP_TRY(cap_stage_out_end(ctx, A_local, (size_t)L * L, dev));
+  CAP_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CAPITAL_OK;
+}
+capital_status_t capital_distribute_random_f64(capital_ctx* ctx, double* A_local, int64_t m, int64_t n, int64_t key) {
+  if (!ctx || !A_local || n <= 0 || m <= 0) return CAPITAL_ERR_INVALID;
+  CAP_CUDA(cudaSetDevice(ctx->device));
+  const int c = ctx->grid.c, d = ctx->grid.d, x = ctx->grid.x, y = ctx->grid.y;
+  const int64_t lr = ceil_div(m, d), lc = ceil_div(n, c);
+  // structure.hpp:110-111: the stream is consumed over the un-padded local extent only
+  const int64_t pad_c = ((n % c != 0) && ((lc - 1) * c + x >= n)) ? lc - 1 : lc;
+  const int64_t pad_r = ((m % d != 0) && ((lr - 1) * d + y >= m)) ? lr - 1 : lr;
+  double* dev;
+  CAP_TRY(cap_stage_out_begin(ctx, A_local, (size_t)lr * lc, "gen_out", &dev));
+  CAP_TRY(gen_random(ctx, ctx->stream, dev, lr, lr, lc, pad_r, pad_c, key));
+  CAP_TRY(cap_stage_out_end(ctx, A_local, (size_t)lr * lc, dev));
+  CAP_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CAPITAL_OK;
+}
+
+// ---- CholInv ----------------------------------------------------------------------------------
+capital_status_t capital_cholinv_factor_f64(capital_ctx* ctx, const double* A_local, int64_t n, const capital_cholinv_args_t* args,
+                                            capital_structure_t ostruct, double* R_local, double* Rinv_local) {
+  if (!ctx) return CAPITAL_ERR_INVALID;
+  if (!A_local || !args || !R_local || !Rinv_local || n <= 0 || args->split <= 0 || args->dir != 'U') {
+    ctx->set_error("cholinv::factor: invalid arguments (split > 0 and dir == 'U' are required, cholinv.hpp:9)");
+    return CAPITAL_ERR_INVALID;
+  }
+  CAP_CUDA(cudaSetDevice(ctx->device));
+  const capital_grid_t& g = ctx->grid;
+  if (g.size > 1) return dist_cholinv_factor(ctx, A_local, n, args, ostruct, R_local, Rinv_local);
+
+  const int64_t L = n, ld = round_up(L, 16);
+  const size_t out_count = ostruct == CAPITAL_UPPERTRI_PACKED ? (size_t)L * (L + 1) / 2 : (size_t)L * L;
+  cudaStream_t st = ctx->stream;
+  CAP_CUDA(cudaEventRecord(ctx->ev_start, st));
+  const double* dA;
+  CAP_TRY(cap_stage_in(ctx, A_local, (size_t)L * L, "A_in", &dA));
+  double *W, *Rm, *Ri, *RiT, *dR, *dRinv;
+  CAP_TRY(ctx->workspace("W", (size_t)ld * L * 8, (void**)&W));
+  CAP_TRY(ctx->workspace("Rm", (size_t)ld * L * 8, (void**)&Rm));
+  CAP_TRY(ctx->workspace("Ri", (size_t)ld * L * 8, (void**)&Ri));
+  CAP_TRY(ctx->workspace("RiT", (size_t)ld * L * 8, (void**)&RiT));
+  CAP_TRY(cap_stage_out_begin(ctx, R_local, out_count, "R_out", &dR));
+  CAP_TRY(cap_stage_out_begin(ctx, Rinv_local, out_count, "Rinv_out", &dRinv));
+  CAP_CUDA(cudaMemsetAsync(ctx->d_info, 0, sizeof(int), st));
+  CAP_CUDA(cudaMemsetAsync(Ri, 0, (size_t)ld * L * 8, st));
+  CAP_CUDA(cudaMemsetAsync(RiT, 0, (size_t)ld * L * 8, st));
+  if (ostruct == CAPITAL_RECT) CAP_CUDA(cudaMemsetAsync(Rm, 0, (size_t)ld * L * 8, st));
+  CAP_TRY(copy_block(ctx, st, L, L, dA, L, W, ld));  // serialize(A -> R), cholinv.hpp:13
+  const int64_t bc = capital_cholinv_bc_dimension(L, g.c, g.d, args->bc_mult_dim);
+  CAP_TRY(cholinv_local(ctx, st, L, W, ld, Rm, ld, Ri, ld, RiT, ld, args->complete_inv != 0, bc, (int)args->split));
+  if (ostruct == CAPITAL_UPPERTRI_PACKED) {
+    CAP_TRY(pack_upper(ctx, st, L, Rm, ld, dR, 0));
+    CAP_TRY(pack_upper(ctx, st, L, Ri, ld, dRinv, 0));
+  } else {
+    CAP_TRY(triu_copy(ctx, st, L, Rm, ld, dR, L, 0));
+    CAP_TRY(triu_copy(ctx, st, L, Ri, ld, dRinv, L, 0));
+  }
+  CAP_TRY(cap_stage_out_end(ctx, R_local, out_count, dR));
+  CAP_TRY(cap_stage_out_end(ctx, Rinv_local, out_count, dRinv));
+  CAP_CUDA(cudaEventRecord(ctx->ev_stop, st));
+  return cap_check_info(ctx);
+}
+
+capital_status_t capital_cholinv_residual_f64(capital_ctx* ctx, const double* A_local, int64_t n, capital_structure_t structure,
+                                              const double* R_local, double* residual) {
+  if (!ctx || !A_local || !R_local || !residual || n <= 0) return CAPITAL_ERR_INVALID;
+  CAP_CUDA(cudaSetDevice(ctx->device));
+  const capital_grid_t& g = ctx->grid;
+  if (g.size > 1) return dist_cholinv_residual(ctx, A_local, n, structure, R_local, residual);
+  const int64_t L = n, ld = round_up(L, 16);
+  cudaStream_t st = ctx->stream;
+  const size_t r_count = structure == CAPITAL_UPPERTRI_PACKED ? (size_t)L * (L + 1) / 2 : (size_t)L * L;
+  const double *dA, *dRin;
+  CAP_TRY(cap_stage_in(ctx, A_local, (size_t)L * L, "A_in", &dA));
+  CAP_TRY(cap_stage_in(ctx, R_local, r_count, "R_in", &dRin));
+  double *E, *Rr;
+  CAP_TRY(ctx->workspace("W", (size_t)ld * L * 8, (void**)&E));
+  CAP_TRY(ctx->workspace("Rm", (size_t)ld * L * 8, (void**)&Rr));
+  if (structure == CAPITAL_UPPERTRI_PACKED) CAP_TRY(unpack_upper(ctx, st, L, dRin, Rr, ld));
+  else CAP_TRY(triu_copy(ctx, st, L, dRin, L, Rr, ld, 0));  // util::remove_triangle, validate.hpp:11
+  CAP_TRY(copy_block(ctx, st, L, L, dA, L, E, ld));
+  CAP_CUDA(cudaMemsetAsync(ctx->d_scalars, 0, 2 * sizeof(double), st));
+  CAP_TRY(sumsq_block(ctx, st, L, L, E, ld, 1, 0, 0, 1, ctx->d_scalars + 1));  // control: sum_upper A^2
+  // E = R^T R - A on the upper tiles (validate.hpp:35 with gemm(T,N,1,-1))
+  CAP_TRY(gemm_tn(ctx, st, L, L, L, 1.0, Rr, ld, Rr, ld, -1.0, E, ld,
+                  CAPITAL_GEMM_A_UPPER | CAPITAL_GEMM_B_UPPER | CAPITAL_GEMM_C_UPPER));
+  CAP_TRY(sumsq_block(ctx, st, L, L, E, ld, 1, 0, 0, 1, ctx->d_scalars));
+  double h[2];
+  CAP_CUDA(cudaMemcpyAsync(h, ctx->d_scalars, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CAP_CUDA(cudaStreamSynchronize(st));
+  *residual = sqrt(h[0]) / sqrt(h[1]);  // util.hpp:51
+  return CAPITAL_OK;
+}
+
+// ---- CholeskyQR2 ------------------------------------------------------------------------------
+capital_status_t capital_cacqr_factor_f64(capital_ctx* ctx, const double* A_local, int64_t m, int64_t n, int num_iter,
+                                          const capital_cholinv_args_t* ci_args, capital_structure_t rstruct, double* Q_local,
+                                          double* R_local) {
+  if (!ctx) return CAPITAL_ERR_INVALID;
+  if (!A_local || !Q_local || !R_local || m <= 0 || n <= 0 || num_iter < 1 || num_iter > 2) {
+    ctx->set_error("cacqr::factor: invalid arguments");
+    return CAPITAL_ERR_INVALID;
+  }
+  CAP_CUDA(cudaSetDevice(ctx->device));
+  return dist_cacqr_factor(ctx, A_local, m, n, num_iter, ci_args, rstruct, Q_local, R_local);
+}
+capital_status_t capital_cacqr_residual_f64(capital_ctx* ctx, const double* A_local, int64_t m, int64_t n, const double* Q_local,
+                                            capital_structure_t rstruct, const double* R_local, double* residual,
+                                            double* orthogonality) {
+  if (!ctx || !A_local || !Q_local || !R_local || !residual || !orthogonality) return CAPITAL_ERR_INVALID;
+  CAP_CUDA(cudaSetDevice(ctx->device));
+  return dist_cacqr_residual(ctx, A_local, m, n, Q_local, rstruct, R_local, residual, orthogonality);
+}
+
+// ---- leaf-engine seam -------------------------------------------------------------------------
+capital_status_t capital_blas_gemm_tn_f64(capital_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
+                                          const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags) {
+  if (!ctx || !A || !B || !C) return CAPITAL_ERR_INVALID;
+  CAP_CUDA(cudaSetDevice(ctx->device));
+  if (!cap_is_device_ptr(A) || !cap_is_device_ptr(B) || !cap_is_device_ptr(C)) {
+    ctx->set_error("capital_blas_gemm_tn_f64 takes device pointers");
+    return CAPITAL_ERR_INVALID;
+  }
+  return gemm_tn(ctx, ctx->stream, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags);
+}
+capital_status_t capital_lapack_potrf_trtri_f64(capital_ctx* ctx, int64_t n, const double* A, int64_t lda, double* R, int64_t ldr,
+                                                double* Rinv, int64_t ldri) {
+  if (!ctx || !A || !R || !Rinv || n <= 0 || lda < n || ldr < n || ldri < n) return CAPITAL_ERR_INVALID;
+  CAP_CUDA(cudaSetDevice(ctx->device));
+  if (!cap_is_device_ptr(A) || !cap_is_device_ptr(R) || !cap_is_device_ptr(Rinv)) return CAPITAL_ERR_INVALID;
+  if ((ldr & 1) || (ldri & 1)) { ctx->set_error("potrf_trtri: ldr, ldri must be even"); return CAPITAL_ERR_INVALID; }
+  cudaStream_t st = ctx->stream;
+  const int64_t ld = round_up(n, 16);
+  double *W, *RiT;
+  CAP_TRY(ctx->workspace("bcW", (size_t)ld * n * 8, (void**)&W));
+  CAP_TRY(ctx->workspace("bcRiT", (size_t)ld * n * 8, (void**)&RiT));
+  CAP_CUDA(cudaMemsetAsync(ctx->d_info, 0, sizeof(int), st));
+  CAP_TRY(copy_block(ctx, st, n, n, A, lda, W, ld));
+  CAP_TRY(zero_block(ctx, st, n, n, R, ldr));
+  CAP_TRY(zero_block(ctx, st, n, n, Rinv, ldri));
+  CAP_CUDA(cudaMemsetAsync(RiT, 0, (size_t)ld * n * 8, st));
+  CAP_TRY(cholinv_local(ctx, st, n, W, ld, R, ldr, Rinv, ldri, RiT, ld, true, n, 1));
+  return cap_check_info(ctx);
+}
+
+}  // extern "C"

@@ -1,0 +1,108 @@
+// capital_b200 -- shared declarations for the CUDA translation units (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <map>
+#include "../../include/capital_b200.h"
+
+#define CAP_CUDA(call)                                                                                    \
+  do {                                                                                                     \
+    cudaError_t e__ = (call);                                                                              \
+    if (e__ != cudaSuccess) {                                                                              \
+      ctx->set_error(std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" +         \
+                     std::to_string(__LINE__) + ")");                                                      \
+      return CAPITAL_ERR_CUDA;                                                                             \
+    }                                                                                                      \
+  } while (0)
+
+#define CAP_TRY(call)                                  \
+  do {                                                 \
+    capital_status_t s__ = (call);                     \
+    if (s__ != CAPITAL_OK) return s__;                 \
+  } while (0)
+
+typedef CUresult (*cuTensorMapEncodeTiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                              CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                              CUtensorMapFloatOOBfill);
+
+struct DeviceBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+struct capital_ctx {
+  capital_grid_t grid{};
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;   // main stream (caller's or owned)
+  cudaStream_t side = nullptr;     // side stream for off-critical-path products
+  bool own_stream = false;
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_fork = nullptr, ev_join = nullptr;
+  cuTensorMapEncodeTiled_fn encode = nullptr;
+  capital_counters_t counters{};
+  std::string err;
+  int* d_info = nullptr;           // device flag: first non-SPD pivot (0 = ok)
+  double* d_scalars = nullptr;     // device scratch for reductions (16 doubles)
+  std::map<std::string, DeviceBuf> pool;  // named, grow-only workspace (the reference's `info` tables, cholinv.h:35-40)
+  // pinned staging for host-pointer callers
+  void* pinned = nullptr;
+  size_t pinned_bytes = 0;
+  // NCCL (dlopen'ed; see comm.cu)
+  void* nccl_lib = nullptr;
+  void* comm_world = nullptr;
+  void* comm_row = nullptr;
+  void* comm_col = nullptr;
+  void* comm_depth = nullptr;
+  void* comm_slice = nullptr;
+
+  void set_error(const std::string& s) { err = s; }
+  capital_status_t workspace(const std::string& name, size_t bytes, void** out);
+  capital_status_t pinned_buf(size_t bytes, void** out);
+};
+
+// ---- gemm_tn.cu -------------------------------------------------------------------------------
+capital_status_t gemm_tn(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
+                         int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags);
+
+capital_status_t gemm_tn_splitk(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
+                                int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int flags);
+
+// ---- layout.cu --------------------------------------------------------------------------------
+capital_status_t transpose_block(capital_ctx* ctx, cudaStream_t st, int64_t rows, int64_t cols, const double* src,
+                                 int64_t lds, double* dst, int64_t ldd, double scale);
+capital_status_t copy_block(capital_ctx* ctx, cudaStream_t st, int64_t rows, int64_t cols, const double* src, int64_t lds,
+                            double* dst, int64_t ldd);
+capital_status_t zero_block(capital_ctx* ctx, cudaStream_t st, int64_t rows, int64_t cols, double* dst, int64_t ldd);
+capital_status_t pack_upper(capital_ctx* ctx, cudaStream_t st, int64_t n, const double* src, int64_t lds, double* packed,
+                            int zero_diag);
+capital_status_t unpack_upper(capital_ctx* ctx, cudaStream_t st, int64_t n, const double* packed, double* dst, int64_t ldd);
+capital_status_t triu_copy(capital_ctx* ctx, cudaStream_t st, int64_t n, const double* src, int64_t lds, double* dst,
+                           int64_t ldd, int zero_diag);
+capital_status_t gen_symmetric(capital_ctx* ctx, cudaStream_t st, double* A, int64_t ld, int64_t lrows, int64_t lcols,
+                               int64_t n_global, int x, int y, int d, int diag_dom);
+capital_status_t gen_random(capital_ctx* ctx, cudaStream_t st, double* A, int64_t ld, int64_t lrows, int64_t lcols,
+                            int64_t pad_rows, int64_t pad_cols, int64_t key);
+// sum of squares over the (global-)upper part (or everything) of a local block; accumulates into out[0]
+capital_status_t sumsq_block(capital_ctx* ctx, cudaStream_t st, int64_t rows, int64_t cols, const double* a, int64_t ld,
+                             int upper_mode, int x, int y, int d, double* out);
+capital_status_t sub_identity_local(capital_ctx* ctx, cudaStream_t st, int64_t n, double* a, int64_t ld);
+
+// ---- leaf.cu ----------------------------------------------------------------------------------
+// potrf('U') + trtri('U','N') of one nb x nb block (nb <= LEAF_MAX) in shared memory.
+constexpr int LEAF_MAX = 64;
+capital_status_t leaf_cholinv(capital_ctx* ctx, cudaStream_t st, int nb, const double* W, int64_t ldw, double* R, int64_t ldr,
+                              double* Ri, int64_t ldri, double* RiT, int64_t ldrit);
+
+// ---- cholinv.cu -------------------------------------------------------------------------------
+// local (single-GPU) recursive CholInv on dense n x n blocks; W is destroyed (Schur complements).
+capital_status_t cholinv_local(capital_ctx* ctx, cudaStream_t st, int64_t n, double* W, int64_t ldw, double* R, int64_t ldr,
+                               double* Ri, int64_t ldri, double* RiT, int64_t ldrit, bool complete_top, int64_t bc, int split);
+
+static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -1,0 +1,528 @@
+// Multi-GPU schedules: one process per GPU, NCCL over NVLink/NVSwitch in place of the reference's MPI.
+//
+//  * CholInv on the reference's c x d x d grid (c == d): every SUMMA of cholinv::invoke (summa.hpp:46-161) becomes
+//      fetch X block from (y,z,z) and Y block from (x,z,z)   [util::transpose + row/column MPI_Bcast, summa.hpp:185,193]
+//      local DMMA product on the k = z (mod d) slice          [cblas_dgemm / dtrmm,                   summa.hpp:64,143]
+//      depth all-reduce of the partial result                 [MPI_Allreduce over depth,              summa.hpp:236]
+//    and the base case is the replicate-everything policy (cholinv/policy.h:160-224): all-gather the d^2 local
+//    blocks inside the slice, factor the dense block redundantly, keep the own cyclic part (zeros below the
+//    global diagonal -- the slots the reference's benchmarked NoReplication policy leaves stale at P > 1).
+//  * CholeskyQR2 1D (c == 1): local Gram (split-K DMMA), one all-reduce of n x n, replicated potrf+trtri, local apply
+//    (cacqr.hpp:5-29,172-193; cacqr/policy.h:78-85).
+//
+// NCCL is dlopen'ed ("libnccl.so.2": the copy torch already mapped when the caller is a torch process, else the
+// system one) so that the library has no link-time dependency and never mixes two NCCL builds in one process.
+#include "dist.cuh"
+#include <dlfcn.h>
+#include <math.h>
+
+namespace {
+
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSuccess = 0 };
+enum { ncclFloat64 = 8 };
+enum { ncclSum = 0 };
+
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  int (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, void*) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+
+NcclApi& nccl() {
+  static NcclApi api;
+  return api;
+}
+
+bool nccl_load(std::string* why) {
+  NcclApi& a = nccl();
+  if (a.lib) return true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    a.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (a.lib) break;
+  }
+  if (!a.lib) { *why = std::string("dlopen(libnccl.so.2) failed: ") + dlerror(); return false; }
+#define LD(field, sym)                                                   \
+  *(void**)(&a.field) = dlsym(a.lib, sym);                               \
+  if (!a.field) { *why = std::string("missing NCCL symbol ") + sym; a.lib = nullptr; return false; }
+  LD(GetUniqueId, "ncclGetUniqueId"); LD(CommInitRank, "ncclCommInitRank"); LD(CommSplit, "ncclCommSplit");
+  LD(CommDestroy, "ncclCommDestroy"); LD(AllReduce, "ncclAllReduce"); LD(AllGather, "ncclAllGather");
+  LD(Broadcast, "ncclBroadcast"); LD(Send, "ncclSend"); LD(Recv, "ncclRecv"); LD(GroupStart, "ncclGroupStart");
+  LD(GroupEnd, "ncclGroupEnd"); LD(GetErrorString, "ncclGetErrorString");
+#undef LD
+  return true;
+}
+
+#define CAP_NCCL(call)                                                                                              \
+  do {                                                                                                               \
+    int r__ = (call);                                                                                                \
+    if (r__ != ncclSuccess) {                                                                                        \
+      ctx->set_error(std::string(#call) + ": " + nccl().GetErrorString(r__) + " (" + __FILE__ + ":" +                \
+                     std::to_string(__LINE__) + ")");                                                                \
+      return CAPITAL_ERR_COMM;                                                                                       \
+    }                                                                                                                \
+  } while (0)
+
+inline int rank_of(const capital_grid_t& g, int x, int y, int z) { return y * g.c * g.d + x * g.c + z; }  // topology.h:81-83 inverted
+
+// ---- small kernels used only by the distributed schedules ---------------------------------------------------
+// C = beta * C + P on an s_m x s_n block (upper_only: local i <= j entries only)
+__global__ void axpby_kernel(long long rows, long long cols, const double* __restrict__ P, long long ldp, double beta, double* __restrict__ C,
+                             long long ldc, int upper_only) {
+  const long long total = rows * cols;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long c = idx / rows, r = idx - c * rows;
+    if (upper_only && r > c) continue;
+    const double v = P[c * ldp + r];
+    C[c * ldc + r] = beta == 0.0 ? v : beta * C[c * ldc + r] + v;
+  }
+}
+// gathered[(x' + d y')] = local block (s x s, ld lds) of slice rank x' + d y'  ->  dense (s d) x (s d) block, upper part
+// (util::block_to_cyclic_*, util.hpp:56-133)
+__global__ void blocks_to_dense_kernel(int s, int d, const double* __restrict__ gathered, long long lds, double* __restrict__ dense,
+                                       long long ldd) {
+  const long long b = (long long)s * d, total = b * b;
+  const long long blk = lds * s;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long gx = idx / b, gy = idx - gx * b;  // col, row
+    double v = 0.0;
+    if (gy <= gx) {
+      const int xo = (int)(gx % d), yo = (int)(gy % d);
+      v = gathered[(xo + (long long)d * yo) * blk + (gx / d) * lds + (gy / d)];
+    }
+    dense[gx * ldd + gy] = v;
+  }
+}
+// own cyclic part of a dense block: loc(j, i) = dense(y + d j, x + d i)   (util::cyclic_to_local, util.hpp:135-164)
+// transposed != 0: loc(j, i) = dense(x' ...) of the TRANSPOSED dense matrix, i.e. dense(x + d i, y + d j)^T handled by caller
+__global__ void dense_to_local_kernel(int s, int d, int x, int y, const double* __restrict__ dense, long long ldd, double* __restrict__ loc,
+                                      long long ldl) {
+  const long long total = (long long)s * s;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long i = idx / s, j = idx - i * s;
+    loc[i * ldl + j] = dense[(x + (long long)d * i) * ldd + (y + (long long)d * j)];
+  }
+}
+
+inline int grid_for(const capital_ctx* ctx, long long total) {
+  long long b = (total + 255) / 256;
+  const long long cap = (long long)ctx->num_sms * 8;
+  return (int)(b > cap ? cap : (b < 1 ? 1 : b));
+}
+
+struct Dist {
+  capital_ctx* ctx;
+  cudaStream_t st;
+  const capital_grid_t& g;
+  int64_t L, ld;
+  double *W, *R, *Ri, *RiT;
+  int64_t bc_local;
+  int split;
+  // contiguous transfer buffers
+  double *bufX, *bufY, *bufP, *bufS;  // fetched X, fetched Y, partial/all-reduced product, send staging (2 blocks)
+  ncclComm_t world, depth, slice;
+};
+
+// pack a (rows x cols) window into a contiguous buffer with even leading dimension
+inline int64_t packed_ld(int64_t rows) { return round_up(rows, 2); }
+
+// One distributed product  C <- beta*C + alpha * X^T Y  (all matrices are windows of cyclically distributed globals;
+// local windows: X: k x m, Y: k x n, C: m x n).  X and Y are the LOCAL windows of this rank; the blocks actually
+// multiplied are the ones owned by (y,z,z) and (x,z,z).
+capital_status_t product(Dist& D, int64_t m, int64_t n, int64_t k, double alpha, const double* X, int64_t ldx, const double* Y,
+                         int64_t ldy, double beta, double* C, int64_t ldc, int flags) {
+  capital_ctx* ctx = D.ctx;
+  const capital_grid_t& g = D.g;
+  const int d = g.d, me = g.rank;
+  const int64_t ldk = packed_ld(k);
+  const int srcX = rank_of(g, g.y, g.z, g.z);  // owner of X rows = z, cols = y
+  const int srcY = rank_of(g, g.x, g.z, g.z);  // owner of Y rows = z, cols = x
+  const bool iAmXsrc = (g.y == g.z);           // my block (cols x, rows y=z) is needed by row y' = x of my layer
+  const bool iAmYsrc = (g.y == g.z);           // my block is needed by column x of my layer
+  const double* Xuse = X; int64_t ldxu = ldx;
+  const double* Yuse = Y; int64_t ldyu = ldy;
+  // stage outgoing blocks contiguously
+  double* sendX = D.bufS;
+  double* sendY = D.bufS + ldk * (m > n ? m : n);
+  bool needSendX = false, needSendY = false;
+  if (iAmXsrc) for (int xx = 0; xx < d; xx++) if (rank_of(g, xx, g.x, g.z) != me) needSendX = true;
+  if (iAmYsrc) for (int yy = 0; yy < d; yy++) if (rank_of(g, g.x, yy, g.z) != me) needSendY = true;
+  if (needSendX) CAP_TRY(copy_block(ctx, D.st, k, m, X, ldx, sendX, ldk));
+  if (needSendY) CAP_TRY(copy_block(ctx, D.st, k, n, Y, ldy, sendY, ldk));
+  CAP_NCCL(nccl().GroupStart());
+  if (iAmXsrc)  // destinations: all (xx, y' = my x, z)
+    for (int xx = 0; xx < d; xx++) {
+      const int dst = rank_of(g, xx, g.x, g.z);
+      if (dst != me) CAP_NCCL(nccl().Send(sendX, (size_t)ldk * m, ncclFloat64, dst, D.world, D.st));
+    }
+  if (iAmYsrc)  // destinations: all (x' = my x, yy, z)
+    for (int yy = 0; yy < d; yy++) {
+      const int dst = rank_of(g, g.x, yy, g.z);
+      if (dst != me) CAP_NCCL(nccl().Send(sendY, (size_t)ldk * n, ncclFloat64, dst, D.world, D.st));
+    }
+  if (srcX != me) { CAP_NCCL(nccl().Recv(D.bufX, (size_t)ldk * m, ncclFloat64, srcX, D.world, D.st)); Xuse = D.bufX; ldxu = ldk; }
+  if (srcY != me) { CAP_NCCL(nccl().Recv(D.bufY, (size_t)ldk * n, ncclFloat64, srcY, D.world, D.st)); Yuse = D.bufY; ldyu = ldk; }
+  CAP_NCCL(nccl().GroupEnd());
+  // local product on the k = z slice
+  const int64_t ldp = packed_ld(m);
+  if (flags & CAPITAL_GEMM_C_UPPER) CAP_CUDA(cudaMemsetAsync(D.bufP, 0, (size_t)ldp * n * 8, D.st));
+  CAP_TRY(gemm_tn(ctx, D.st, m, n, k, alpha, Xuse, ldxu, Yuse, ldyu, 0.0, D.bufP, ldp, flags));
+  if (g.c > 1) CAP_NCCL(nccl().AllReduce(D.bufP, D.bufP, (size_t)ldp * n, ncclFloat64, ncclSum, D.depth, D.st));
+  axpby_kernel<<<grid_for(ctx, m * n), 256, 0, D.st>>>(m, n, D.bufP, ldp, beta, C, ldc, (flags & CAPITAL_GEMM_C_UPPER) ? 1 : 0);
+  ctx->counters.kernel_launches++;
+  CAP_CUDA(cudaGetLastError());
+  return CAPITAL_OK;
+}
+
+// global transpose of a local window: dst(local n x m) = [window of the partner (y,x,z)]^T   (util::transpose, util.hpp:232-247,
+// followed by the local transpose the reference defers to its BLAS flags)
+capital_status_t transpose_dist(Dist& D, int64_t rows, int64_t cols, const double* src, int64_t lds, double* dst, int64_t ldd) {
+  capital_ctx* ctx = D.ctx;
+  const capital_grid_t& g = D.g;
+  const int partner = rank_of(g, g.y, g.x, g.z);
+  if (partner == g.rank) return transpose_block(ctx, D.st, rows, cols, src, lds, dst, ldd, 1.0);
+  const int64_t ldr = packed_ld(rows);
+  CAP_TRY(copy_block(ctx, D.st, rows, cols, src, lds, D.bufS, ldr));
+  CAP_NCCL(nccl().GroupStart());
+  CAP_NCCL(nccl().Send(D.bufS, (size_t)ldr * cols, ncclFloat64, partner, D.world, D.st));
+  CAP_NCCL(nccl().Recv(D.bufX, (size_t)ldr * cols, ncclFloat64, partner, D.world, D.st));
+  CAP_NCCL(nccl().GroupEnd());
+  return transpose_block(ctx, D.st, rows, cols, D.bufX, ldr, dst, ldd, 1.0);
+}
+
+// replicate-everything base case on the local window at offset `o` of size s (local); dense size b = s d
+capital_status_t base_case(Dist& D, int64_t o, int64_t s) {
+  capital_ctx* ctx = D.ctx;
+  const capital_grid_t& g = D.g;
+  const int d = g.d;
+  const int64_t b = s * d, ldb = round_up(b, 16), lds = packed_ld(s);
+  double *gath, *dW, *dR, *dRi, *dRiT;
+  CAP_TRY(ctx->workspace("bc_gather", (size_t)lds * s * d * d * 8, (void**)&gath));
+  CAP_TRY(ctx->workspace("bc_W", (size_t)ldb * b * 8, (void**)&dW));
+  CAP_TRY(ctx->workspace("bc_R", (size_t)ldb * b * 8, (void**)&dR));
+  CAP_TRY(ctx->workspace("bc_Ri", (size_t)ldb * b * 8, (void**)&dRi));
+  CAP_TRY(ctx->workspace("bc_RiT", (size_t)ldb * b * 8, (void**)&dRiT));
+  double* Wo = D.W + o * D.ld + o;
+  CAP_TRY(copy_block(ctx, D.st, s, s, Wo, D.ld, D.bufS, lds));
+  CAP_NCCL(nccl().AllGather(D.bufS, gath, (size_t)lds * s, ncclFloat64, D.slice, D.st));  // policy.h:176
+  blocks_to_dense_kernel<<<grid_for(ctx, b * b), 256, 0, D.st>>>((int)s, d, gath, lds, dW, ldb);
+  ctx->counters.kernel_launches++;
+  CAP_CUDA(cudaGetLastError());
+  CAP_CUDA(cudaMemsetAsync(dRi, 0, (size_t)ldb * b * 8, D.st));
+  CAP_CUDA(cudaMemsetAsync(dRiT, 0, (size_t)ldb * b * 8, D.st));
+  CAP_CUDA(cudaMemsetAsync(dR, 0, (size_t)ldb * b * 8, D.st));
+  CAP_TRY(cholinv_local(ctx, D.st, b, dW, ldb, dR, ldb, dRi, ldb, dRiT, ldb, true, b, 1));  // potrf + trtri, policy.h:199-201
+  const int gr = grid_for(ctx, s * s);
+  dense_to_local_kernel<<<gr, 256, 0, D.st>>>((int)s, d, g.x, g.y, dR, ldb, D.R + o * D.ld + o, D.ld);
+  dense_to_local_kernel<<<gr, 256, 0, D.st>>>((int)s, d, g.x, g.y, dRi, ldb, D.Ri + o * D.ld + o, D.ld);
+  dense_to_local_kernel<<<gr, 256, 0, D.st>>>((int)s, d, g.x, g.y, dRiT, ldb, D.RiT + o * D.ld + o, D.ld);
+  ctx->counters.kernel_launches += 3;
+  CAP_CUDA(cudaGetLastError());
+  return CAPITAL_OK;
+}
+
+// cholinv::invoke (cholinv.hpp:87-165) on the local window [o, o+s)
+capital_status_t invoke(Dist& D, int64_t o, int64_t s, bool complete) {
+  capital_ctx* ctx = D.ctx;
+  const int64_t s1 = s >> D.split;
+  if (s <= D.bc_local || s1 < D.split || s1 == 0) return base_case(D, o, s);
+  const int64_t s2 = s - s1, ld = D.ld;
+  double* W12 = D.W + (o + s1) * ld + o;
+  double* W21 = D.W + o * ld + (o + s1);
+  double* W22 = D.W + (o + s1) * ld + (o + s1);
+  double* R12 = D.R + (o + s1) * ld + o;
+  double* Ri11 = D.Ri + o * ld + o;
+  double* Ri12 = D.Ri + (o + s1) * ld + o;
+  double* Ri22 = D.Ri + (o + s1) * ld + (o + s1);
+  double* RiT11 = D.RiT + o * ld + o;
+  double* RiT21 = D.RiT + o * ld + (o + s1);
+  CAP_TRY(invoke(D, o, s1, true));
+  CAP_TRY(product(D, s1, s2, s1, 1.0, Ri11, ld, W12, ld, 0.0, R12, ld, CAPITAL_GEMM_A_UPPER));       // cholinv.hpp:116-122
+  CAP_TRY(product(D, s2, s2, s1, -1.0, R12, ld, R12, ld, 1.0, W22, ld, CAPITAL_GEMM_C_UPPER));        // :131-134
+  CAP_TRY(invoke(D, o + s1, s2, true));
+  if (complete) {                                                                                       // :147-155
+    CAP_TRY(product(D, s2, s1, s1, 1.0, R12, ld, RiT11, ld, 0.0, W21, ld, CAPITAL_GEMM_B_LOWER));
+    CAP_TRY(product(D, s1, s2, s2, -1.0, W21, ld, Ri22, ld, 0.0, Ri12, ld, CAPITAL_GEMM_B_UPPER));
+    CAP_TRY(transpose_dist(D, s1, s2, Ri12, ld, RiT21, ld));
+  }
+  return CAPITAL_OK;
+}
+
+capital_status_t need_comm(capital_ctx* ctx) {
+  if (ctx->grid.size > 1 && !ctx->comm_world) {
+    ctx->set_error("multi-GPU grid but capital_comm_init was not called");
+    return CAPITAL_ERR_COMM;
+  }
+  return CAPITAL_OK;
+}
+
+capital_status_t allreduce_scalars(capital_ctx* ctx, double* dptr, int count) {
+  if (ctx->grid.size > 1) CAP_NCCL(nccl().AllReduce(dptr, dptr, count, ncclFloat64, ncclSum, (ncclComm_t)ctx->comm_world, ctx->stream));
+  return CAPITAL_OK;
+}
+
+}  // namespace
+
+extern "C" capital_status_t capital_comm_unique_id(void* out128) {
+  std::string why;
+  if (!out128 || !nccl_load(&why)) return CAPITAL_ERR_COMM;
+  ncclUniqueId id;
+  if (nccl().GetUniqueId(&id) != ncclSuccess) return CAPITAL_ERR_COMM;
+  memcpy(out128, &id, 128);
+  return CAPITAL_OK;
+}
+
+extern "C" capital_status_t capital_comm_init(capital_ctx* ctx, const void* uid) {
+  if (!ctx || !uid) return CAPITAL_ERR_INVALID;
+  CAP_CUDA(cudaSetDevice(ctx->device));
+  std::string why;
+  if (!nccl_load(&why)) { ctx->set_error(why); return CAPITAL_ERR_COMM; }
+  const capital_grid_t& g = ctx->grid;
+  ncclUniqueId id;
+  memcpy(&id, uid, 128);
+  ncclComm_t world = nullptr, depth = nullptr, slice = nullptr;
+  CAP_NCCL(nccl().CommInitRank(&world, g.size, id, g.rank));
+  ctx->comm_world = world;
+  // sub-communicators of topo::square (topology.h:84-94): depth = same (x,y), slice = same z
+  CAP_NCCL(nccl().CommSplit(world, g.y * g.d + g.x, g.z, &depth, nullptr));
+  CAP_NCCL(nccl().CommSplit(world, g.z, g.y * g.d + g.x, &slice, nullptr));
+  ctx->comm_depth = depth;
+  ctx->comm_slice = slice;
+  return CAPITAL_OK;
+}
+
+void dist_destroy(capital_ctx* ctx) {
+  if (!nccl().lib) return;
+  if (ctx->comm_depth) nccl().CommDestroy((ncclComm_t)ctx->comm_depth);
+  if (ctx->comm_slice) nccl().CommDestroy((ncclComm_t)ctx->comm_slice);
+  if (ctx->comm_world) nccl().CommDestroy((ncclComm_t)ctx->comm_world);
+  ctx->comm_depth = ctx->comm_slice = ctx->comm_world = nullptr;
+}
+
+capital_status_t dist_cholinv_factor(capital_ctx* ctx, const double* A_local, int64_t n, const capital_cholinv_args_t* args,
+                                     capital_structure_t ostruct, double* R_local, double* Rinv_local) {
+  const capital_grid_t& g = ctx->grid;
+  CAP_TRY(need_comm(ctx));
+  if (g.c != g.d || n % g.d != 0) {
+    ctx->set_error("distributed cholinv needs the reference's cubic grid (c == d, summa.hpp:16-31) and d | n");
+    return CAPITAL_ERR_UNSUPPORTED;
+  }
+  const int64_t L = n / g.d, ld = round_up(L, 16);
+  const size_t out_count = ostruct == CAPITAL_UPPERTRI_PACKED ? (size_t)L * (L + 1) / 2 : (size_t)L * L;
+  cudaStream_t st = ctx->stream;
+  CAP_CUDA(cudaEventRecord(ctx->ev_start, st));
+  const double* dA;
+  CAP_TRY(cap_stage_in(ctx, A_local, (size_t)L * L, "A_in", &dA));
+  Dist D{ctx, st, g};
+  D.L = L; D.ld = ld; D.split = (int)args->split;
+  D.bc_local = capital_cholinv_bc_dimension(L, g.c, g.d, args->bc_mult_dim) / g.d;
+  D.world = (ncclComm_t)ctx->comm_world; D.depth = (ncclComm_t)ctx->comm_depth; D.slice = (ncclComm_t)ctx->comm_slice;
+  double *dR, *dRinv;
+  CAP_TRY(ctx->workspace("W", (size_t)ld * L * 8, (void**)&D.W));
+  CAP_TRY(ctx->workspace("Rm", (size_t)ld * L * 8, (void**)&D.R));
+  CAP_TRY(ctx->workspace("Ri", (size_t)ld * L * 8, (void**)&D.Ri));
+  CAP_TRY(ctx->workspace("RiT", (size_t)ld * L * 8, (void**)&D.RiT));
+  const int64_t half = L - (L >> D.split) > (L >> D.split) ? L - (L >> D.split) : (L >> D.split);
+  const size_t blk = (size_t)packed_ld(half) * half * 8 + 4096;
+  CAP_TRY(ctx->workspace("xferX", blk, (void**)&D.bufX));
+  CAP_TRY(ctx->workspace("xferY", blk, (void**)&D.bufY));
+  CAP_TRY(ctx->workspace("xferP", blk, (void**)&D.bufP));
+  CAP_TRY(ctx->workspace("xferS", 2 * blk, (void**)&D.bufS));
+  CAP_TRY(cap_stage_out_begin(ctx, R_local, out_count, "R_out", &dR));
+  CAP_TRY(cap_stage_out_begin(ctx, Rinv_local, out_count, "Rinv_out", &dRinv));
+  CAP_CUDA(cudaMemsetAsync(ctx->d_info, 0, sizeof(int), st));
+  CAP_CUDA(cudaMemsetAsync(D.Ri, 0, (size_t)ld * L * 8, st));
+  CAP_CUDA(cudaMemsetAsync(D.RiT, 0, (size_t)ld * L * 8, st));
+  CAP_CUDA(cudaMemsetAsync(D.R, 0, (size_t)ld * L * 8, st));
+  CAP_TRY(copy_block(ctx, st, L, L, dA, L, D.W, ld));
+  CAP_TRY(invoke(D, 0, L, args->complete_inv != 0));
+  if (ostruct == CAPITAL_UPPERTRI_PACKED) {
+    CAP_TRY(pack_upper(ctx, st, L, D.R, ld, dR, 0));
+    CAP_TRY(pack_upper(ctx, st, L, D.Ri, ld, dRinv, 0));
+  } else {
+    CAP_TRY(triu_copy(ctx, st, L, D.R, ld, dR, L, 0));
+    CAP_TRY(triu_copy(ctx, st, L, D.Ri, ld, dRinv, L, 0));
+  }
+  CAP_TRY(cap_stage_out_end(ctx, R_local, out_count, dR));
+  CAP_TRY(cap_stage_out_end(ctx, Rinv_local, out_count, dRinv));
+  CAP_CUDA(cudaEventRecord(ctx->ev_stop, st));
+  return cap_check_info(ctx);
+}
+
+capital_status_t dist_cholinv_residual(capital_ctx* ctx, const double* A_local, int64_t n, capital_structure_t structure,
+                                       const double* R_local, double* residual) {
+  const capital_grid_t& g = ctx->grid;
+  CAP_TRY(need_comm(ctx));
+  if (g.c != g.d || n % g.d != 0) return CAPITAL_ERR_UNSUPPORTED;
+  const int64_t L = n / g.d, ld = round_up(L, 16);
+  cudaStream_t st = ctx->stream;
+  const size_t r_count = structure == CAPITAL_UPPERTRI_PACKED ? (size_t)L * (L + 1) / 2 : (size_t)L * L;
+  const double *dA, *dRin;
+  CAP_TRY(cap_stage_in(ctx, A_local, (size_t)L * L, "A_in", &dA));
+  CAP_TRY(cap_stage_in(ctx, R_local, r_count, "R_in", &dRin));
+  Dist D{ctx, st, g};
+  D.L = L; D.ld = ld; D.split = 1; D.bc_local = L;
+  D.world = (ncclComm_t)ctx->comm_world; D.depth = (ncclComm_t)ctx->comm_depth; D.slice = (ncclComm_t)ctx->comm_slice;
+  double *E, *Rr;
+  CAP_TRY(ctx->workspace("W", (size_t)ld * L * 8, (void**)&E));
+  CAP_TRY(ctx->workspace("Rm", (size_t)ld * L * 8, (void**)&Rr));
+  const size_t blk = (size_t)packed_ld(L) * L * 8 + 4096;
+  CAP_TRY(ctx->workspace("xferX", blk, (void**)&D.bufX));
+  CAP_TRY(ctx->workspace("xferY", blk, (void**)&D.bufY));
+  CAP_TRY(ctx->workspace("xferP", blk, (void**)&D.bufP));
+  CAP_TRY(ctx->workspace("xferS", 2 * blk, (void**)&D.bufS));
+  if (structure == CAPITAL_UPPERTRI_PACKED) CAP_TRY(unpack_upper(ctx, st, L, dRin, Rr, ld));
+  else CAP_TRY(triu_copy(ctx, st, L, dRin, L, Rr, ld, 0));
+  if (g.y > g.x) {  // util::remove_triangle (validate.hpp:11): local diagonal is below the global diagonal there
+    CAP_TRY(triu_copy(ctx, st, L, Rr, ld, Rr, ld, 1));
+  }
+  CAP_TRY(copy_block(ctx, st, L, L, dA, L, E, ld));
+  CAP_CUDA(cudaMemsetAsync(ctx->d_scalars, 0, 2 * sizeof(double), st));
+  CAP_TRY(sumsq_block(ctx, st, L, L, E, ld, 1, g.x, g.y, g.d, ctx->d_scalars + 1));
+  // E = R^T R - A  (validate.hpp:35).  No C_UPPER: on ranks with y > x the local diagonal is outside the global upper part anyway.
+  CAP_TRY(product(D, L, L, L, 1.0, Rr, ld, Rr, ld, -1.0, E, ld, CAPITAL_GEMM_A_UPPER | CAPITAL_GEMM_B_UPPER));
+  CAP_TRY(sumsq_block(ctx, st, L, L, E, ld, 1, g.x, g.y, g.d, ctx->d_scalars));
+  CAP_TRY(allreduce_scalars(ctx, ctx->d_scalars, 2));
+  double h[2];
+  CAP_CUDA(cudaMemcpyAsync(h, ctx->d_scalars, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CAP_CUDA(cudaStreamSynchronize(st));
+  *residual = sqrt(h[0]) / sqrt(h[1]);
+  return CAPITAL_OK;
+}
+
+// ---- CholeskyQR2, 1D --------------------------------------------------------------------------------------------
+namespace {
+struct Qr {
+  capital_ctx* ctx;
+  cudaStream_t st;
+  int64_t lr, n, ldq, ldn, ldt;
+  double *Q, *Qt, *Qt2, *G, *W, *R1, *R2, *Ri, *RiT, *Rt;
+};
+
+// sweep_1d (cacqr.hpp:5-29): G = Q^T Q, all-reduce, R = chol(G), Rinv, Q <- Q Rinv.  R lands in `Rout`.
+capital_status_t sweep(Qr& q, double* Rout) {
+  capital_ctx* ctx = q.ctx;
+  cudaStream_t st = q.st;
+  const int64_t n = q.n, lr = q.lr;
+  CAP_CUDA(cudaMemsetAsync(q.G, 0, (size_t)q.ldn * n * 8, st));
+  CAP_TRY(gemm_tn_splitk(ctx, st, n, n, lr, 1.0, q.Q, q.ldq, q.Q, q.ldq, q.G, q.ldn, CAPITAL_GEMM_C_UPPER));  // dsyrk 'U','T' (:15)
+  if (ctx->grid.size > 1)
+    CAP_NCCL(nccl().AllReduce(q.G, q.G, (size_t)q.ldn * n, ncclFloat64, ncclSum, (ncclComm_t)ctx->comm_world, st));  // policy.h:82
+  CAP_CUDA(cudaMemsetAsync(q.Ri, 0, (size_t)q.ldn * n * 8, st));
+  CAP_CUDA(cudaMemsetAsync(q.RiT, 0, (size_t)q.ldn * n * 8, st));
+  CAP_CUDA(cudaMemsetAsync(Rout, 0, (size_t)q.ldn * n * 8, st));
+  CAP_TRY(cholinv_local(ctx, st, n, q.G, q.ldn, Rout, q.ldn, q.Ri, q.ldn, q.RiT, q.ldn, true, n, 1));  // potrf + trtri (:20-22)
+  // Q <- Q Rinv (dtrmm Right/Upper/NoTrans, :25) as (Q Rinv)^T = Rinv^T Q^T : A = Rinv (upper), B = Q^T
+  CAP_TRY(transpose_block(ctx, st, lr, n, q.Q, q.ldq, q.Qt, q.ldt, 1.0));
+  CAP_TRY(gemm_tn(ctx, st, n, lr, n, 1.0, q.Ri, q.ldn, q.Qt, q.ldt, 0.0, q.Qt2, q.ldt, CAPITAL_GEMM_A_UPPER));
+  CAP_TRY(transpose_block(ctx, st, n, lr, q.Qt2, q.ldt, q.Q, q.ldq, 1.0));
+  return CAPITAL_OK;
+}
+}  // namespace
+
+capital_status_t dist_cacqr_factor(capital_ctx* ctx, const double* A_local, int64_t m, int64_t n, int num_iter,
+                                   const capital_cholinv_args_t* ci_args, capital_structure_t rstruct, double* Q_local, double* R_local) {
+  (void)ci_args;
+  const capital_grid_t& g = ctx->grid;
+  CAP_TRY(need_comm(ctx));
+  if (g.c != 1) {
+    ctx->set_error("cacqr: only the 1D grid (c == 1, cacqr.hpp:229) is implemented; 3D / tunable grids are a later row of the scope table");
+    return CAPITAL_ERR_UNSUPPORTED;
+  }
+  const int64_t lr = ceil_div(m, g.d);
+  cudaStream_t st = ctx->stream;
+  CAP_CUDA(cudaEventRecord(ctx->ev_start, st));
+  Qr q{ctx, st};
+  q.lr = lr; q.n = n; q.ldq = round_up(lr, 16); q.ldn = round_up(n, 16); q.ldt = q.ldn;
+  const double* dA;
+  CAP_TRY(cap_stage_in(ctx, A_local, (size_t)lr * n, "A_in", &dA));
+  const size_t r_count = rstruct == CAPITAL_UPPERTRI_PACKED ? (size_t)n * (n + 1) / 2 : (size_t)n * n;
+  double *dQ, *dR;
+  CAP_TRY(cap_stage_out_begin(ctx, Q_local, (size_t)lr * n, "Q_out", &dQ));
+  CAP_TRY(cap_stage_out_begin(ctx, R_local, r_count, "R_out", &dR));
+  CAP_TRY(ctx->workspace("qrQ", (size_t)q.ldq * n * 8, (void**)&q.Q));
+  CAP_TRY(ctx->workspace("qrQt", (size_t)q.ldt * lr * 8, (void**)&q.Qt));
+  CAP_TRY(ctx->workspace("qrQt2", (size_t)q.ldt * lr * 8, (void**)&q.Qt2));
+  const size_t nn = (size_t)q.ldn * n * 8;
+  CAP_TRY(ctx->workspace("qrG", nn, (void**)&q.G));
+  CAP_TRY(ctx->workspace("qrR1", nn, (void**)&q.R1));
+  CAP_TRY(ctx->workspace("qrR2", nn, (void**)&q.R2));
+  CAP_TRY(ctx->workspace("qrRi", nn, (void**)&q.Ri));
+  CAP_TRY(ctx->workspace("qrRiT", nn, (void**)&q.RiT));
+  CAP_TRY(ctx->workspace("qrRt", nn, (void**)&q.Rt));
+  CAP_CUDA(cudaMemsetAsync(ctx->d_info, 0, sizeof(int), st));
+  CAP_TRY(copy_block(ctx, st, lr, n, dA, lr, q.Q, q.ldq));  // Q <- A (cacqr.hpp:226)
+  CAP_TRY(sweep(q, q.R1));
+  const double* Rfinal = q.R1;
+  if (num_iter > 1) {
+    CAP_TRY(sweep(q, q.R2));
+    // R = R2 R1 (dtrmm, cacqr.hpp:185-187) = (R2^T)^T R1 : A = R2^T (lower), B = R1 (upper)
+    CAP_TRY(transpose_block(ctx, st, n, n, q.R2, q.ldn, q.Rt, q.ldn, 1.0));
+    CAP_TRY(gemm_tn(ctx, st, n, n, n, 1.0, q.Rt, q.ldn, q.R1, q.ldn, 0.0, q.G, q.ldn,
+                    CAPITAL_GEMM_A_LOWER | CAPITAL_GEMM_B_UPPER | CAPITAL_GEMM_C_UPPER));
+    Rfinal = q.G;
+  }
+  if (rstruct == CAPITAL_UPPERTRI_PACKED) CAP_TRY(pack_upper(ctx, st, n, Rfinal, q.ldn, dR, 0));
+  else CAP_TRY(triu_copy(ctx, st, n, Rfinal, q.ldn, dR, n, 0));
+  CAP_TRY(copy_block(ctx, st, lr, n, q.Q, q.ldq, dQ, lr));
+  CAP_TRY(cap_stage_out_end(ctx, Q_local, (size_t)lr * n, dQ));
+  CAP_TRY(cap_stage_out_end(ctx, R_local, r_count, dR));
+  CAP_CUDA(cudaEventRecord(ctx->ev_stop, st));
+  return cap_check_info(ctx);
+}
+
+capital_status_t dist_cacqr_residual(capital_ctx* ctx, const double* A_local, int64_t m, int64_t n, const double* Q_local,
+                                     capital_structure_t rstruct, const double* R_local, double* residual, double* orthogonality) {
+  const capital_grid_t& g = ctx->grid;
+  CAP_TRY(need_comm(ctx));
+  if (g.c != 1) return CAPITAL_ERR_UNSUPPORTED;
+  const int64_t lr = ceil_div(m, g.d);
+  cudaStream_t st = ctx->stream;
+  const int64_t ldq = round_up(lr, 16), ldn = round_up(n, 16);
+  const size_t r_count = rstruct == CAPITAL_UPPERTRI_PACKED ? (size_t)n * (n + 1) / 2 : (size_t)n * n;
+  const double *dA, *dQ, *dRin;
+  CAP_TRY(cap_stage_in(ctx, A_local, (size_t)lr * n, "A_in", &dA));
+  CAP_TRY(cap_stage_in(ctx, Q_local, (size_t)lr * n, "Q_in", &dQ));
+  CAP_TRY(cap_stage_in(ctx, R_local, r_count, "R_in", &dRin));
+  double *Q, *Qt, *Et, *R, *G;
+  CAP_TRY(ctx->workspace("qrQ", (size_t)ldq * n * 8, (void**)&Q));
+  CAP_TRY(ctx->workspace("qrQt", (size_t)ldn * lr * 8, (void**)&Qt));
+  CAP_TRY(ctx->workspace("qrQt2", (size_t)ldn * lr * 8, (void**)&Et));
+  CAP_TRY(ctx->workspace("qrR1", (size_t)ldn * n * 8, (void**)&R));
+  CAP_TRY(ctx->workspace("qrG", (size_t)ldn * n * 8, (void**)&G));
+  CAP_TRY(copy_block(ctx, st, lr, n, dQ, lr, Q, ldq));
+  if (rstruct == CAPITAL_UPPERTRI_PACKED) CAP_TRY(unpack_upper(ctx, st, n, dRin, R, ldn));
+  else CAP_TRY(triu_copy(ctx, st, n, dRin, n, R, ldn, 0));
+  CAP_CUDA(cudaMemsetAsync(ctx->d_scalars, 0, 3 * sizeof(double), st));
+  // residual (validate.hpp:37-52): ||QR - A||_F / ||A||_F, via (QR)^T - A^T = R^T Q^T - A^T
+  CAP_TRY(transpose_block(ctx, st, lr, n, Q, ldq, Qt, ldn, 1.0));
+  CAP_TRY(transpose_block(ctx, st, lr, n, dA, lr, Et, ldn, 1.0));
+  CAP_TRY(sumsq_block(ctx, st, n, lr, Et, ldn, 0, 0, 0, 1, ctx->d_scalars + 1));
+  CAP_TRY(gemm_tn(ctx, st, n, lr, n, 1.0, R, ldn, Qt, ldn, -1.0, Et, ldn, CAPITAL_GEMM_A_UPPER));
+  CAP_TRY(sumsq_block(ctx, st, n, lr, Et, ldn, 0, 0, 0, 1, ctx->d_scalars));
+  // orthogonality (validate.hpp:7-35): ||Q^T Q - I||_F / sqrt(n^2)
+  CAP_CUDA(cudaMemsetAsync(G, 0, (size_t)ldn * n * 8, st));
+  CAP_TRY(gemm_tn_splitk(ctx, st, n, n, lr, 1.0, Q, ldq, Q, ldq, G, ldn, 0));
+  if (g.size > 1) CAP_NCCL(nccl().AllReduce(G, G, (size_t)ldn * n, ncclFloat64, ncclSum, (ncclComm_t)ctx->comm_world, st));
+  CAP_TRY(sub_identity_local(ctx, st, n, G, ldn));
+  CAP_TRY(sumsq_block(ctx, st, n, n, G, ldn, 0, 0, 0, 1, ctx->d_scalars + 2));
+  CAP_TRY(allreduce_scalars(ctx, ctx->d_scalars, 2));  // numerator/denominator of the residual are row-partitioned sums
+  double h[3];
+  CAP_CUDA(cudaMemcpyAsync(h, ctx->d_scalars, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CAP_CUDA(cudaStreamSynchronize(st));
+  *residual = sqrt(h[0]) / sqrt(h[1]);
+  *orthogonality = sqrt(h[2]) / sqrt((double)n * (double)n);
+  return CAPITAL_OK;
+}

@@ -1,0 +1,132 @@
+"""GPU parity of the factorization entry points (single GPU) against the reference's own dumps (tests/golden),
+the oracle restatement, and size-independent properties at larger n."""
+import json, os
+import numpy as np
+import pytest
+import torch
+import capital_b200 as cb
+from capital_b200 import _lib
+from oracle import capital_oracle as co
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load(name):
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    return json.loads(str(z["meta"])), z
+
+
+@pytest.fixture(scope="module")
+def topo():
+    return cb.topo.square(1, 0, 1)
+
+
+@pytest.mark.parametrize("name", ["cholinv_p1_n96_ci1", "cholinv_p1_n128_ci0"])
+def test_cholinv_matches_reference_dump(topo, name):
+    meta, z = load(name)
+    n = meta["n"]
+    A = cb.matrix(n, n, 1, 1).distribute_symmetric(topo)
+    assert np.array_equal(A.data.cpu().numpy(), z["A_0"])
+    args = cb.cholinv.info(meta["complete_inv"], meta["split"], meta["bc_mult_dim"], "U")
+    cb.cholinv.factor(A, args, topo)
+    r, ri = args.R.cpu().numpy(), args.Rinv.cpu().numpy()
+    assert np.abs(r - z["R_0"]).max() <= 1e-13 * np.abs(z["R_0"]).max()
+    assert np.abs(ri - z["Rinv_0"]).max() <= 1e-13 * np.abs(z["Rinv_0"]).max()
+    if not meta["complete_inv"]:
+        assert np.array_equal(ri == 0, z["Rinv_0"] == 0)  # same zero block (cholinv.hpp:147)
+    assert cb.cholinv.residual(A, args, topo) < 1e-14
+
+
+@pytest.mark.parametrize("n,ci,bcm", [(64, 1, 0), (200, 1, -1), (512, 0, -2), (777, 1, -2), (1000, 0, -3), (2048, 0, -2), (2048, 1, -2)])
+@pytest.mark.parametrize("serialize", [True, False])
+def test_cholinv_matches_oracle(topo, n, ci, bcm, serialize):
+    A = cb.matrix(n, n, 1, 1).distribute_symmetric(topo)
+    args = cb.cholinv.info(ci, 1, bcm, "U", serialize=serialize)
+    cb.cholinv.factor(A, args, topo)
+    a = co.spd_global(n)
+    r_o, ri_o = co.cholinv(a, bool(ci), 1, co.bc_dimension(n, 1, 1, bcm))
+    R = cb.cholinv.construct_R(args, topo).cpu().numpy()
+    Ri = cb.cholinv.construct_Rinv(args, topo).cpu().numpy()
+    assert np.abs(R - r_o).max() <= 2e-13 * np.abs(r_o).max()
+    assert np.abs(Ri - ri_o).max() <= 2e-13 * np.abs(ri_o).max()
+    assert np.array_equal(np.tril(R, -1), np.zeros_like(R)) and np.array_equal(np.tril(Ri, -1), np.zeros_like(Ri))
+    res = cb.cholinv.residual(A, args, topo)
+    assert res <= 1e-12 and abs(res - co.cholesky_residual(a, R)) < 1e-15
+
+
+def test_cholinv_host_pointers_and_reuse(topo):
+    """reference-facing call: pinned host buffers in, pinned host buffers out; repeated calls reuse the workspaces."""
+    n = 640
+    a = torch.from_numpy(np.asfortranarray(co.spd_global(n)).ravel(order="F").copy()).pin_memory()
+    A = cb.matrix(n, n, 1, 1, data=a)
+    args = cb.cholinv.info(1, 1, -2, "U")
+    ctx = topo.context()
+    for _ in range(2):
+        ctx.reset_counters()
+        cb.cholinv.factor(A, args, topo)
+        cnt = ctx.counters()
+        assert cnt.h2d_bytes == n * n * 8 and cnt.d2h_bytes == 2 * (n * (n + 1) // 2) * 8 and cnt.kernel_launches > 0
+    assert not args.R.is_cuda
+    r_o, ri_o = co.cholinv(co.spd_global(n), True, 1, co.bc_dimension(n, 1, 1, -2))
+    assert np.abs(co.unpack_upper(args.R.numpy(), n) - r_o).max() < 1e-12
+    assert np.abs(co.unpack_upper(args.Rinv.numpy(), n) - ri_o).max() < 1e-13
+
+
+def test_cholinv_rejects_non_spd(topo):
+    n = 256
+    A = cb.matrix(n, n, 1, 1).distribute_symmetric(topo)
+    A.view2d()[100, 100] = -1.0
+    with pytest.raises(_lib.CapitalError) as e:
+        cb.cholinv.factor(A, cb.cholinv.info(1, 1, -1, "U"), topo)
+    assert e.value.status == _lib.ERR_NOT_SPD
+
+
+@pytest.mark.parametrize("n", [4096, 8192])
+def test_cholinv_large_properties(topo, n):
+    """size-independent properties: residual, R Rinv = I on the diagonal blocks, idempotent re-factorization."""
+    A = cb.matrix(n, n, 1, 1).distribute_symmetric(topo)
+    args = cb.cholinv.info(0, 1, -3, "U", serialize=False)
+    cb.cholinv.factor(A, args, topo)
+    assert cb.cholinv.residual(A, args, topo) <= 1e-12
+    R, Ri = cb.cholinv.construct_R(args), cb.cholinv.construct_Rinv(args)
+    h = n // 2
+    eye = torch.eye(h, dtype=torch.float64, device="cuda")
+    assert (Ri[:h, :h] @ R[:h, :h] - eye).abs().max().item() < 1e-12
+    assert (Ri[h:, h:] @ R[h:, h:] - eye).abs().max().item() < 1e-12
+    assert torch.count_nonzero(Ri[:h, h:]).item() == 0
+    keep = args.R.clone()
+    cb.cholinv.factor(A, args, topo)
+    assert torch.equal(keep, args.R)  # deterministic
+
+
+@pytest.mark.parametrize("name", ["cacqr_p1_m512_n32"])
+def test_cacqr_matches_reference_dump(name):
+    meta, z = load(name)
+    m, n = meta["m"], meta["n"]
+    topo = cb.topo.rect(1, 0, 1)
+    A = cb.matrix(n, m, 1, 1).distribute_random(topo, 0)
+    assert np.array_equal(A.data.cpu().numpy(), z["A_0"])
+    args = cb.cacqr.info(2, cb.cholinv.info(0, 1, 0, "U"))
+    cb.cacqr.factor(A, args, topo)
+    assert np.abs(args.R.cpu().numpy() - z["R_0"]).max() < 1e-12 * np.abs(z["R_0"]).max()
+    assert np.abs(args.Q.cpu().numpy() - z["Q_0"]).max() < 1e-12
+    res, orth = cb.cacqr.validate(A, args, topo)
+    assert res < 1e-14 and orth < 1e-15
+
+
+@pytest.mark.parametrize("m,n,it", [(4096, 64, 2), (10000, 100, 2), (65536, 256, 2), (3000, 48, 1)])
+def test_cacqr_matches_oracle(m, n, it):
+    topo = cb.topo.rect(1, 0, 1)
+    A = cb.matrix(n, m, 1, 1).distribute_random(topo, 3)
+    args = cb.cacqr.info(it, cb.cholinv.info(0, 1, 0, "U"))
+    cb.cacqr.factor(A, args, topo)
+    a = co.random_local(m, n, 1, 1, 0, 0, 3)
+    qs, r = co.cacqr_1d([a], it)
+    Q, R = cb.cacqr.construct_Q(args).cpu().numpy(), cb.cacqr.construct_R(args).cpu().numpy()
+    assert np.abs(R - r).max() < 1e-11 * np.abs(r).max()
+    assert np.abs(Q - qs[0]).max() < 1e-11
+    res, orth = cb.cacqr.validate(A, args, topo)
+    assert res < 1e-13
+    assert orth < (1e-14 if it == 2 else 1e-12)
+    assert abs(res - co.qr_residual(a, Q, R)) < 1e-15
