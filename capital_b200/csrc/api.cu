@@ -141,6 +141,7 @@ void capital_destroy(capital_ctx* ctx) {
   if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
   if (ctx->side) cudaStreamDestroy(ctx->side);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -166,6 +167,26 @@ capital_status_t capital_last_factor_ms(const capital_ctx* ctx_, float* ms) {
   capital_ctx* ctx = const_cast<capital_ctx*>(ctx_);
   if (!ctx || !ms) return CAPITAL_ERR_INVALID;
   CAP_CUDA(cudaEventElapsedTime(ms, ctx->ev_start, ctx->ev_stop));
+  return CAPITAL_OK;
+}
+
+capital_status_t capital_profile_begin(capital_ctx* ctx) {
+  if (!ctx) return CAPITAL_ERR_INVALID;
+  ctx->profiling = true; ctx->prof_used = 0; ctx->prof_recs.clear();
+  return CAPITAL_OK;
+}
+capital_status_t capital_profile_end(capital_ctx* ctx, double* kernel_ms, double* kernel_flops, int64_t* launches) {
+  if (!ctx || !kernel_ms || !kernel_flops || !launches) return CAPITAL_ERR_INVALID;
+  ctx->profiling = false;
+  CAP_CUDA(cudaStreamSynchronize(ctx->stream));
+  double ms = 0, fl = 0;
+  for (auto& r : ctx->prof_recs) {
+    float t = 0;
+    CAP_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+    ms += t; fl += r.flops;
+  }
+  *kernel_ms = ms; *kernel_flops = fl; *launches = (int64_t)ctx->prof_recs.size();
+  ctx->prof_recs.clear(); ctx->prof_used = 0;
   return CAPITAL_OK;
 }
 

@@ -61,6 +61,22 @@ struct capital_ctx {
   void* comm_depth = nullptr;
   void* comm_slice = nullptr;
 
+  // per-launch timing of the dominant kernel (gemm_tn 128x128), off by default
+  struct ProfRec { cudaEvent_t e0, e1; double flops; };
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_pool;
+  size_t prof_used = 0;
+  std::vector<ProfRec> prof_recs;
+  capital_status_t prof_event(cudaEvent_t* out) {
+    if (prof_used == prof_pool.size()) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) { err = "cudaEventCreate failed"; return CAPITAL_ERR_CUDA; }
+      prof_pool.push_back(e);
+    }
+    *out = prof_pool[prof_used++];
+    return CAPITAL_OK;
+  }
+
   void set_error(const std::string& s) { err = s; }
   capital_status_t workspace(const std::string& name, size_t bytes, void** out);
   capital_status_t pinned_buf(size_t bytes, void** out);

@@ -288,13 +288,28 @@ capital_status_t gemm_tn(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n
   if (m >= (1LL << 31) || n >= (1LL << 31) || k >= (1LL << 31) - 16) return CAPITAL_ERR_INVALID;
   ctx->counters.kernel_launches++;
   ctx->counters.gemm_launches++;
-  {  // executed flops (for reporting): count k extent per tile approximately via structure flags
-    double f = 2.0 * (double)m * (double)n * (double)k;
-    if (flags & (CAPITAL_GEMM_A_UPPER | CAPITAL_GEMM_A_LOWER | CAPITAL_GEMM_B_UPPER | CAPITAL_GEMM_B_LOWER)) f *= 0.5;
-    if (flags & CAPITAL_GEMM_C_UPPER) f *= 0.5;
-    ctx->counters.gemm_flops += f;
-  }
+  // algorithmic flops of this product (structure exploited exactly, not tile-rounded)
+  double f = 2.0 * (double)m * (double)n * (double)k;
+  const bool atri = flags & (CAPITAL_GEMM_A_UPPER | CAPITAL_GEMM_A_LOWER), btri = flags & (CAPITAL_GEMM_B_UPPER | CAPITAL_GEMM_B_LOWER);
+  if (atri && btri) f = 2.0 * (double)m * (double)n * (double)k / 3.0;
+  else if (atri) f = (double)n * (double)m * (double)(m + 1);
+  else if (btri) f = (double)m * (double)n * (double)(n + 1);
+  else if (flags & CAPITAL_GEMM_C_UPPER) f = (double)k * (double)m * (double)(m + 1);
+  ctx->counters.gemm_flops += f;
   const int64_t tiles_big = ceil_div(m, 128) * ceil_div(n, 128);
-  if (tiles_big >= ctx->num_sms) return launch<CfgBig, 128, 128>(ctx, st, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags, 1);
+  if (tiles_big >= ctx->num_sms) {
+    // dominant kernel: optionally bracketed by events on its own stream (capital_profile_begin/end)
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ctx->profiling) {
+      CAP_TRY(ctx->prof_event(&e0)); CAP_TRY(ctx->prof_event(&e1));
+      CAP_CUDA(cudaEventRecord(e0, st));
+    }
+    CAP_TRY((launch<CfgBig, 128, 128>(ctx, st, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags, 1)));
+    if (ctx->profiling) {
+      CAP_CUDA(cudaEventRecord(e1, st));
+      ctx->prof_recs.push_back({e0, e1, f});
+    }
+    return CAPITAL_OK;
+  }
   return launch<CfgSmall, 64, 64>(ctx, st, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags, 1);
 }

@@ -89,6 +89,12 @@ capital_status_t capital_synchronize(capital_ctx* ctx);
 /* time (ms) between two library-recorded CUDA events bracketing the last factor call, on its stream */
 capital_status_t capital_last_factor_ms(const capital_ctx* ctx, float* ms);
 
+/* Per-launch CUDA-event timing of the dominant kernel (the 128x128 DMMA GEMM) on the stream it is launched on:
+ * begin arms it; end synchronizes and returns the summed launch durations, the algorithmic flops of those
+ * launches (structure exploited) and their count.  Used by bench.py for the roofline line. */
+capital_status_t capital_profile_begin(capital_ctx* ctx);
+capital_status_t capital_profile_end(capital_ctx* ctx, double* kernel_ms, double* kernel_flops, int64_t* launches);
+
 /* ---- generators (device kernels; bit-exact with the reference's drand48-based ones) ---------- */
 /* matrix::distribute_symmetric(x, y, d, d, key, diagonallyDominant) -- structure.hpp:69-103. */
 capital_status_t capital_distribute_symmetric_f64(capital_ctx* ctx, double* A_local, int64_t n_global,

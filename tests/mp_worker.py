@@ -1,0 +1,93 @@
+"""Multi-GPU parity worker (run under torch.distributed.run, one process per GPU).  Exits non-zero on mismatch.
+
+Checks the distributed CholInv (reference's 2x2x2 grid) and 1D CholeskyQR2 against the reference's own per-rank dumps
+(tests/golden/*_p8_*.npz), the oracle restatement, and the validators; rank 0 prints a summary line.
+"""
+import json, os, sys
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import capital_b200 as cb
+from oracle import capital_oracle as co
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def load(name):
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    return json.loads(str(z["meta"])), z
+
+
+def main():
+    rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(lr)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    ok = True
+    msgs = []
+    if world == 8:
+        topo = cb.topo.square(8, rank, 2)
+        # --- reference dumps, elementwise ---
+        for name in ("cholinv_p8_n128_ci0", "cholinv_p8_n192_ci1"):
+            meta, z = load(name)
+            n = meta["n"]
+            A = cb.matrix(n, n, 2, 2).distribute_symmetric(topo)
+            ok &= np.array_equal(A.data.cpu().numpy(), z[f"A_{rank}"])
+            args = cb.cholinv.info(meta["complete_inv"], meta["split"], meta["bc_mult_dim"], "U")
+            cb.cholinv.factor(A, args, topo)
+            er = np.abs(args.R.cpu().numpy() - z[f"R_{rank}"]).max() / np.abs(z[f"R_{rank}"]).max()
+            ei = np.abs(args.Rinv.cpu().numpy() - z[f"Rinv_{rank}"]).max() / np.abs(z[f"Rinv_{rank}"]).max()
+            same_zeros = np.array_equal(args.Rinv.cpu().numpy() == 0, z[f"Rinv_{rank}"] == 0)
+            res = cb.cholinv.residual(A, args, topo)
+            ok &= er < 1e-13 and ei < 1e-13 and same_zeros and res < 1e-14
+            msgs.append(f"{name}: dR={er:.1e} dRinv={ei:.1e} zeros={same_zeros} res={res:.1e}")
+        # --- oracle restatement at a size with several distributed levels + ragged local sizes ---
+        for n, ci, bcm in ((1024, 1, -2), (1536, 0, -3), (4096, 0, -3)):
+            A = cb.matrix(n, n, 2, 2).distribute_symmetric(topo)
+            args = cb.cholinv.info(ci, 1, bcm, "U")
+            cb.cholinv.factor(A, args, topo)
+            L = n // 2
+            r_o, ri_o = co.cholinv(co.spd_global(n), bool(ci), 1, co.bc_dimension(L, 2, 2, bcm), d=2)
+            R = cb.cholinv.construct_R(args).cpu().numpy()
+            Ri = cb.cholinv.construct_Rinv(args).cpu().numpy()
+            er = np.abs(R - np.triu(co.cyclic_local(r_o, 2, 2, topo.x, topo.y))).max() / np.abs(r_o).max()
+            ei = np.abs(Ri - np.triu(co.cyclic_local(ri_o, 2, 2, topo.x, topo.y))).max() / np.abs(ri_o).max()
+            zd = (topo.y <= topo.x) or (np.all(np.diag(R) == 0) and np.all(np.diag(Ri) == 0))
+            res = cb.cholinv.residual(A, args, topo)
+            ok &= er < 2e-13 and ei < 2e-13 and zd and res < 1e-12
+            msgs.append(f"oracle n={n} ci={ci}: dR={er:.1e} dRinv={ei:.1e} zero-diag-slots={zd} res={res:.1e}")
+    # --- 1D CholeskyQR2 on all ranks ---
+    qt = cb.topo.rect(world, rank, 1)
+    if world == 8:
+        meta, z = load("cacqr_p8_1d_m1024_n32")
+        m, n = meta["m"], meta["n"]
+        A = cb.matrix(n, m, 1, world).distribute_random(qt, rank)
+        ok &= np.array_equal(A.data.cpu().numpy(), z[f"A_{rank}"])
+        qa = cb.cacqr.info(2, cb.cholinv.info(0, 1, 0, "U"))
+        cb.cacqr.factor(A, qa, qt)
+        er = np.abs(qa.R.cpu().numpy() - z[f"R_{rank}"]).max() / np.abs(z[f"R_{rank}"]).max()
+        eq = np.abs(qa.Q.cpu().numpy() - z[f"Q_{rank}"]).max()
+        res, orth = cb.cacqr.validate(A, qa, qt)
+        ok &= er < 1e-12 and eq < 1e-12 and res < 1e-14 and orth < 1e-15
+        msgs.append(f"cacqr golden: dR={er:.1e} dQ={eq:.1e} res={res:.1e} orth={orth:.1e}")
+    m, n = 1 << 17, 128
+    A = cb.matrix(n, m, 1, world).distribute_random(qt, rank)
+    qa = cb.cacqr.info(2, cb.cholinv.info(0, 1, 0, "U"))
+    cb.cacqr.factor(A, qa, qt)
+    res, orth = cb.cacqr.validate(A, qa, qt)
+    ok &= res < 1e-13 and orth < 1e-14
+    msgs.append(f"cacqr m={m} n={n} P={world}: res={res:.1e} orth={orth:.1e}")
+    flag = torch.tensor([0 if ok else 1], device="cuda")
+    dist.all_reduce(flag)
+    if rank == 0:
+        print(("MP_OK " if flag.item() == 0 else "MP_FAIL ") + " | ".join(msgs), flush=True)
+    dist.barrier()
+    cb.topo.release_contexts()
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 0 else 1)
+
+
+if __name__ == "__main__":
+    main()
