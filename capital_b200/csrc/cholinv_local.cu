@@ -29,6 +29,7 @@ capital_status_t rec(capital_ctx* ctx, cudaStream_t st, int64_t n, double* W, in
   int64_t s1;
   if (n > bc && (n >> split) >= split && (n >> split) > 0 && (n > LEAF_MAX || !complete)) s1 = n >> split;
   else if (n <= LEAF_MAX) return leaf_cholinv(ctx, st, (int)n, W, ldw, R, ldr, Ri, ldri, RiT, ldrit);
+  else if (n <= BASECASE_MAX && n % 64 == 0 && complete) return basecase_cholinv(ctx, st, (int)n, W, ldw, R, ldr, Ri, ldri, RiT, ldrit);
   else s1 = split_point(n);
   const int64_t s2 = n - s1;
   double* W12 = W + s1 * ldw;

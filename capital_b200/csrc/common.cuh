@@ -112,6 +112,9 @@ capital_status_t sub_identity_local(capital_ctx* ctx, cudaStream_t st, int64_t n
 // ---- leaf.cu ----------------------------------------------------------------------------------
 // potrf('U') + trtri('U','N') of one nb x nb block (nb <= LEAF_MAX) in shared memory.
 constexpr int LEAF_MAX = 64;
+constexpr int BASECASE_MAX = 512;  // largest block handled by the one-launch cluster kernel (multiple of 64)
+capital_status_t basecase_cholinv(capital_ctx* ctx, cudaStream_t st, int nb, double* W, int64_t ldw, double* R, int64_t ldr,
+                                  double* Ri, int64_t ldri, double* RiT, int64_t ldrit);
 capital_status_t leaf_cholinv(capital_ctx* ctx, cudaStream_t st, int nb, const double* W, int64_t ldw, double* R, int64_t ldr,
                               double* Ri, int64_t ldri, double* RiT, int64_t ldrit);
 
