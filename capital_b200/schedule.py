@@ -1,0 +1,35 @@
+"""Host-side description of the multi-GPU communication schedule (mirrors capital_b200/csrc/dist.cu).
+
+Pure functions, no GPU: used by the CPU (gloo) tests to run the same rank arithmetic with numpy operands, and as
+documentation of who talks to whom.  Rank <-> (x, y, z) is topo::square layout 0 (topology.h:81-83).
+"""
+from __future__ import annotations
+
+
+def rank_of(c: int, d: int, x: int, y: int, z: int) -> int:
+    return y * c * d + x * c + z
+
+
+def coords(c: int, d: int, rank: int):
+    return (rank % (c * d)) // c, rank // (c * d), rank % c  # x, y, z
+
+
+def summa_plan(c: int, d: int, rank: int) -> dict:
+    """One distributed product C += X^T Y on the cubic grid (c == d), as executed by dist.cu::product():
+    the X block multiplied on (x,y,z) is the local X window of (y,z,z), the Y block the local window of (x,z,z)
+    (util::transpose + row/column MPI_Bcast in the reference, summa.hpp:185,193); partial products are summed over
+    the depth communicator (summa.hpp:236)."""
+    assert c == d
+    x, y, z = coords(c, d, rank)
+    plan = {
+        "src_x": rank_of(c, d, y, z, z),
+        "src_y": rank_of(c, d, x, z, z),
+        "send_x_to": [rank_of(c, d, xx, x, z) for xx in range(d)] if y == z else [],
+        "send_y_to": [rank_of(c, d, x, yy, z) for yy in range(d)] if y == z else [],
+        "depth_group": [rank_of(c, d, x, y, zz) for zz in range(c)],
+        "slice_group": [rank_of(c, d, xx, yy, z) for yy in range(d) for xx in range(d)],  # slice rank = x + d*y
+        "transpose_partner": rank_of(c, d, y, x, z),
+    }
+    plan["send_x_to"] = [r for r in plan["send_x_to"] if r != rank]
+    plan["send_y_to"] = [r for r in plan["send_y_to"] if r != rank]
+    return plan
