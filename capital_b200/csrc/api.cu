@@ -60,6 +60,59 @@ capital_status_t cap_check_info(capital_ctx* ctx) {
   return CAPITAL_OK;
 }
 
+// ---- host-pointer streaming of cholinv::factor (single GPU) ----------------------------------------------------
+namespace {
+struct HostIO {
+  capital_ctx* ctx = nullptr;
+  int64_t L = 0, ld = 0;
+  double *Rm = nullptr, *Ri = nullptr, *dR = nullptr, *dRinv = nullptr, *hR = nullptr, *hRinv = nullptr;
+  bool packed = true;
+  std::vector<std::pair<int64_t, cudaEvent_t>> chunks;  // (col_end, arrived)
+  int64_t waited = 0;
+  int64_t cols_out = 0;
+  cudaEvent_t e_out = nullptr;
+};
+capital_status_t io_event(capital_ctx* ctx, cudaEvent_t* e) {
+  if (ctx->io_used == ctx->io_pool.size()) {
+    cudaEvent_t ev;
+    CAP_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    ctx->io_pool.push_back(ev);
+  }
+  *e = ctx->io_pool[ctx->io_used++];
+  return CAPITAL_OK;
+}
+capital_status_t hostio_need_cols(void* user, cudaStream_t st, int64_t col_end) {
+  HostIO* io = (HostIO*)user;
+  capital_ctx* ctx = io->ctx;
+  if (col_end <= io->waited) return CAPITAL_OK;
+  for (auto& ch : io->chunks)
+    if (ch.first >= col_end) {
+      CAP_CUDA(cudaStreamWaitEvent(st, ch.second, 0));
+      io->waited = ch.first;
+      return CAPITAL_OK;
+    }
+  return CAPITAL_OK;
+}
+// columns [0, s1) of R and Rinv are final: pack them (a contiguous prefix of the packed triangle) and start their D2H
+capital_status_t hostio_left_done(void* user, cudaStream_t st, int64_t s1) {
+  HostIO* io = (HostIO*)user;
+  capital_ctx* ctx = io->ctx;
+  const size_t cnt = (size_t)s1 * (s1 + 1) / 2;
+  CAP_TRY(pack_upper(ctx, st, io->L, io->Rm, io->ld, io->dR, 0, 0, s1));
+  CAP_TRY(pack_upper(ctx, st, io->L, io->Ri, io->ld, io->dRinv, 0, 0, s1));
+  cudaEvent_t e;
+  CAP_TRY(io_event(ctx, &e));
+  CAP_CUDA(cudaEventRecord(e, st));
+  CAP_CUDA(cudaStreamWaitEvent(ctx->copy_out, e, 0));
+  if (io->hR) { CAP_CUDA(cudaMemcpyAsync(io->hR, io->dR, cnt * 8, cudaMemcpyDeviceToHost, ctx->copy_out)); ctx->counters.d2h_bytes += (int64_t)cnt * 8; }
+  if (io->hRinv) { CAP_CUDA(cudaMemcpyAsync(io->hRinv, io->dRinv, cnt * 8, cudaMemcpyDeviceToHost, ctx->copy_out)); ctx->counters.d2h_bytes += (int64_t)cnt * 8; }
+  CAP_TRY(io_event(ctx, &io->e_out));
+  CAP_CUDA(cudaEventRecord(io->e_out, ctx->copy_out));
+  io->cols_out = s1;
+  return CAPITAL_OK;
+}
+}  // namespace
+
 extern "C" {
 
 capital_status_t capital_grid_square(int size, int rank, int c, int layout, int num_chunks, capital_grid_t* out) {
@@ -113,7 +166,12 @@ capital_status_t capital_create(capital_ctx** out, const capital_grid_t* grid, i
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return CAPITAL_ERR_CUDA; }
     ctx->own_stream = true;
   }
-  bool ok = cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) == cudaSuccess;
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // lo = numerically greatest = lowest priority
+  bool ok = cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, prio_lo) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithPriority(&ctx->hi, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaEventCreate(&ctx->ev_start) == cudaSuccess && cudaEventCreate(&ctx->ev_stop) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess;
@@ -143,6 +201,11 @@ void capital_destroy(capital_ctx* ctx) {
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
   if (ctx->side) cudaStreamDestroy(ctx->side);
+  if (ctx->hi) cudaStreamDestroy(ctx->hi);
+  if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+  if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
+  for (cudaEvent_t e : ctx->dep_pool) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->io_pool) cudaEventDestroy(e);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -234,9 +297,8 @@ capital_status_t capital_cholinv_factor_f64(capital_ctx* ctx, const double* A_lo
   const int64_t L = n, ld = round_up(L, 16);
   const size_t out_count = ostruct == CAPITAL_UPPERTRI_PACKED ? (size_t)L * (L + 1) / 2 : (size_t)L * L;
   cudaStream_t st = ctx->stream;
+  ctx->io_used = 0;
   CAP_CUDA(cudaEventRecord(ctx->ev_start, st));
-  const double* dA;
-  CAP_TRY(cap_stage_in(ctx, A_local, (size_t)L * L, "A_in", &dA));
   double *W, *Rm, *Ri, *RiT, *dR, *dRinv;
   CAP_TRY(ctx->workspace("W", (size_t)ld * L * 8, (void**)&W));
   CAP_TRY(ctx->workspace("Rm", (size_t)ld * L * 8, (void**)&Rm));
@@ -248,18 +310,51 @@ capital_status_t capital_cholinv_factor_f64(capital_ctx* ctx, const double* A_lo
   CAP_CUDA(cudaMemsetAsync(Ri, 0, (size_t)ld * L * 8, st));
   CAP_CUDA(cudaMemsetAsync(RiT, 0, (size_t)ld * L * 8, st));
   if (ostruct == CAPITAL_RECT) CAP_CUDA(cudaMemsetAsync(Rm, 0, (size_t)ld * L * 8, st));
-  CAP_TRY(copy_block(ctx, st, L, L, dA, L, W, ld));  // serialize(A -> R), cholinv.hpp:13
+
+  // Host-pointer callers: A streams in by column chunks on a copy stream while the recursion already works on the leading
+  // columns (it consumes W left to right); the finished left half of R / Rinv streams out while the right half computes.
+  HostIO io;
+  io.ctx = ctx; io.L = L; io.ld = ld; io.Rm = Rm; io.Ri = Ri; io.dR = dR; io.dRinv = dRinv;
+  io.hR = (dR != R_local) ? R_local : nullptr; io.hRinv = (dRinv != Rinv_local) ? Rinv_local : nullptr;
+  io.packed = ostruct == CAPITAL_UPPERTRI_PACKED;
+  CholinvHooks hooks{&io, nullptr, nullptr};
+  if (!cap_is_device_ptr(A_local)) {
+    cudaEvent_t e0;
+    CAP_TRY(io_event(ctx, &e0));
+    CAP_CUDA(cudaEventRecord(e0, st));  // W must be free (previous users on st) before the copies land
+    CAP_CUDA(cudaStreamWaitEvent(ctx->copy_in, e0, 0));
+    const int64_t chunk = round_up(ceil_div(L, 16), 64);
+    for (int64_t c0 = 0; c0 < L; c0 += chunk) {
+      const int64_t nc = (c0 + chunk <= L) ? chunk : L - c0;
+      CAP_CUDA(cudaMemcpy2DAsync(W + c0 * ld, (size_t)ld * 8, A_local + c0 * L, (size_t)L * 8, (size_t)L * 8, (size_t)nc,
+                                 cudaMemcpyHostToDevice, ctx->copy_in));
+      cudaEvent_t e;
+      CAP_TRY(io_event(ctx, &e));
+      CAP_CUDA(cudaEventRecord(e, ctx->copy_in));
+      io.chunks.push_back({c0 + nc, e});
+    }
+    ctx->counters.h2d_bytes += (int64_t)L * L * 8;
+    hooks.need_cols = hostio_need_cols;
+  } else {
+    CAP_TRY(copy_block(ctx, st, L, L, A_local, L, W, ld));  // serialize(A -> R), cholinv.hpp:13
+  }
+  if (io.packed && (io.hR || io.hRinv)) hooks.left_done = hostio_left_done;
   const int64_t bc = capital_cholinv_bc_dimension(L, g.c, g.d, args->bc_mult_dim);
-  CAP_TRY(cholinv_local(ctx, st, L, W, ld, Rm, ld, Ri, ld, RiT, ld, args->complete_inv != 0, bc, (int)args->split));
+  CAP_TRY(cholinv_local(ctx, st, L, W, ld, Rm, ld, Ri, ld, RiT, ld, args->complete_inv != 0, bc, (int)args->split, &hooks));
   if (ostruct == CAPITAL_UPPERTRI_PACKED) {
-    CAP_TRY(pack_upper(ctx, st, L, Rm, ld, dR, 0));
-    CAP_TRY(pack_upper(ctx, st, L, Ri, ld, dRinv, 0));
+    const int64_t c0 = io.cols_out;  // columns [0, c0) already packed (and on their way to the host)
+    const size_t off = (size_t)c0 * (c0 + 1) / 2, cnt = out_count - off;
+    CAP_TRY(pack_upper(ctx, st, L, Rm, ld, dR, 0, c0, L));
+    if (io.hR) { CAP_CUDA(cudaMemcpyAsync(io.hR + off, dR + off, cnt * 8, cudaMemcpyDeviceToHost, st)); ctx->counters.d2h_bytes += (int64_t)cnt * 8; }
+    CAP_TRY(pack_upper(ctx, st, L, Ri, ld, dRinv, 0, c0, L));
+    if (io.hRinv) { CAP_CUDA(cudaMemcpyAsync(io.hRinv + off, dRinv + off, cnt * 8, cudaMemcpyDeviceToHost, st)); ctx->counters.d2h_bytes += (int64_t)cnt * 8; }
+    if (io.e_out) CAP_CUDA(cudaStreamWaitEvent(st, io.e_out, 0));  // the early D2H of the left half
   } else {
     CAP_TRY(triu_copy(ctx, st, L, Rm, ld, dR, L, 0));
     CAP_TRY(triu_copy(ctx, st, L, Ri, ld, dRinv, L, 0));
+    CAP_TRY(cap_stage_out_end(ctx, R_local, out_count, dR));
+    CAP_TRY(cap_stage_out_end(ctx, Rinv_local, out_count, dRinv));
   }
-  CAP_TRY(cap_stage_out_end(ctx, R_local, out_count, dR));
-  CAP_TRY(cap_stage_out_end(ctx, Rinv_local, out_count, dRinv));
   CAP_CUDA(cudaEventRecord(ctx->ev_stop, st));
   return cap_check_info(ctx);
 }

@@ -8,6 +8,12 @@
 //   Ri  : out -- R^{-1} (upper);   RiT : out -- (R^{-1})^T (lower), kept so that "Left/Upper/NoTrans" and
 //               "Right/Upper/NoTrans" trmm (cholinv.hpp:150-154) are both A^T B products with K-contiguous operands.
 // Ri and RiT must be zero on entry (the triangular products read whole diagonal tiles).
+//
+// Two streams.  The reference's recursion is strictly sequential; here the chain that the next diagonal block
+// depends on (base cases, R12, and the part of the trailing update the right child's left subtree reads -- "near")
+// runs on a high-priority stream, while work nobody waits for yet (the rest of the trailing update -- "far" -- and
+// T^T of the inverse combine) is queued on a low-priority stream and joined by events exactly where it is consumed.
+// The latency-bound bottom of the recursion then overlaps with DMMA-bound work instead of idling 140 SMs.
 #include "common.cuh"
 
 namespace {
@@ -21,40 +27,105 @@ int64_t split_point(int64_t n) {
   return s1;
 }
 
+struct Rec {
+  capital_ctx* ctx;
+  cudaStream_t M, S;  // critical chain / deferred work
+  double *W, *R, *Ri, *RiT;
+  int64_t ldw, ldr, ldri, ldrit;
+  int64_t bc;
+  int split;
+  const CholinvHooks* hooks;
+  int64_t far_min;  // trailing updates smaller than this are not split
+};
+
 // Levels above the base case (n > bc) split by the reference's rule s1 = n >> split (cholinv.hpp:92,107); it fixes
 // which Rinv block stays zero when complete_inv == 0.  Below it -- the reference's potrf/trtri base case
-// (cholinv.hpp:93-104) -- the recursion continues with 64-aligned halves down to the shared-memory leaf.
-capital_status_t rec(capital_ctx* ctx, cudaStream_t st, int64_t n, double* W, int64_t ldw, double* R, int64_t ldr, double* Ri,
-                     int64_t ldri, double* RiT, int64_t ldrit, bool complete, int64_t bc, int split) {
-  int64_t s1;
-  if (n > bc && (n >> split) >= split && (n >> split) > 0 && (n > LEAF_MAX || !complete)) s1 = n >> split;
-  else if (n <= LEAF_MAX) return leaf_cholinv(ctx, st, (int)n, W, ldw, R, ldr, Ri, ldri, RiT, ldrit);
-  else if (n <= BASECASE_MAX && n % 64 == 0 && complete) return basecase_cholinv(ctx, st, (int)n, W, ldw, R, ldr, Ri, ldri, RiT, ldrit);
-  else s1 = split_point(n);
+// (cholinv.hpp:93-104) -- the recursion continues with 64-aligned halves down to the cluster / leaf kernels.
+// Returns 0 when the block is handled by a single kernel.
+int64_t choose_split(const Rec& r, int64_t n, bool complete) {
+  if (n > r.bc && (n >> r.split) >= r.split && (n >> r.split) > 0 && (n > LEAF_MAX || !complete)) return n >> r.split;
+  if (n <= LEAF_MAX) return 0;
+  if (n <= BASECASE_MAX && n % 64 == 0 && complete) return 0;
+  return split_point(n);
+}
+
+capital_status_t new_event(capital_ctx* ctx, cudaEvent_t* e) {
+  if (ctx->dep_used == ctx->dep_pool.size()) {
+    cudaEvent_t ev;
+    CAP_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    ctx->dep_pool.push_back(ev);
+  }
+  *e = ctx->dep_pool[ctx->dep_used++];
+  return CAPITAL_OK;
+}
+
+// o: offset of the node inside the buffers (diagonal position); pending: event the node's first use of data outside
+// its leading sub-block has to wait for (the parent's deferred "far" update), or nullptr.
+capital_status_t rec(Rec& r, int64_t o, int64_t n, bool complete, cudaEvent_t pending, int depth) {
+  capital_ctx* ctx = r.ctx;
+  double* W = r.W + o * r.ldw + o;
+  double* R = r.R + o * r.ldr + o;
+  double* Ri = r.Ri + o * r.ldri + o;
+  double* RiT = r.RiT + o * r.ldrit + o;
+  const int64_t ldw = r.ldw, ldr = r.ldr, ldri = r.ldri, ldrit = r.ldrit;
+  const int64_t s1 = choose_split(r, n, complete);
+  if (s1 == 0) {
+    if (r.hooks && r.hooks->need_cols) CAP_TRY(r.hooks->need_cols(r.hooks->user, r.M, o + n));
+    if (pending) CAP_CUDA(cudaStreamWaitEvent(r.M, pending, 0));
+    if (n <= LEAF_MAX) return leaf_cholinv(ctx, r.M, (int)n, W, ldw, R, ldr, Ri, ldri, RiT, ldrit);
+    return basecase_cholinv(ctx, r.M, (int)n, W, ldw, R, ldr, Ri, ldri, RiT, ldrit);
+  }
   const int64_t s2 = n - s1;
   double* W12 = W + s1 * ldw;
   double* W21 = W + s1;  // dead lower-left block: scratch for T^T (s2 x s1)
   double* W22 = W + s1 * ldw + s1;
   double* R12 = R + s1 * ldr;
-  double* R22 = R + s1 * ldr + s1;
   double* Ri12 = Ri + s1 * ldri;
   double* Ri22 = Ri + s1 * ldri + s1;
   double* RiT21 = RiT + s1;
-  double* RiT22 = RiT + s1 * ldrit + s1;
 
-  CAP_TRY(rec(ctx, st, s1, W, ldw, R, ldr, Ri, ldri, RiT, ldrit, true, bc, split));
+  CAP_TRY(rec(r, o, s1, true, nullptr, depth + 1));
+  if (depth == 0 && r.hooks && r.hooks->left_done) CAP_TRY(r.hooks->left_done(r.hooks->user, r.M, s1));
+  if (r.hooks && r.hooks->need_cols) CAP_TRY(r.hooks->need_cols(r.hooks->user, r.M, o + n));
+  if (pending) CAP_CUDA(cudaStreamWaitEvent(r.M, pending, 0));  // the parent's deferred update covers W12 and W22
   // "trsm" via the inverse (cholinv.hpp:116-122): R12 = Rinv11^T A12
-  CAP_TRY(gemm_tn(ctx, st, s1, s2, s1, 1.0, Ri, ldri, W12, ldw, 0.0, R12, ldr, CAPITAL_GEMM_A_UPPER));
-  // trailing update (cholinv.hpp:131-134): A22 -= R12^T R12, upper tiles only
-  CAP_TRY(gemm_tn(ctx, st, s2, s2, s1, -1.0, R12, ldr, R12, ldr, 1.0, W22, ldw, CAPITAL_GEMM_C_UPPER));
-  CAP_TRY(rec(ctx, st, s2, W22, ldw, R22, ldr, Ri22, ldri, RiT22, ldrit, true, bc, split));
+  CAP_TRY(gemm_tn(ctx, r.M, s1, s2, s1, 1.0, Ri, ldri, W12, ldw, 0.0, R12, ldr, CAPITAL_GEMM_A_UPPER));
+  cudaEvent_t e_r12 = nullptr, e_tt = nullptr, e_far = nullptr;
+  const bool use_side = r.S != nullptr && s1 >= 256;
+  if (use_side) {
+    CAP_TRY(new_event(ctx, &e_r12));
+    CAP_CUDA(cudaEventRecord(e_r12, r.M));
+    CAP_CUDA(cudaStreamWaitEvent(r.S, e_r12, 0));
+  }
+  cudaStream_t tS = use_side ? r.S : r.M;
+  // trailing update (cholinv.hpp:131-134): A22 -= R12^T R12, upper tiles only.
+  // near = what the right child's left subtree reads (leading h x h block), far = everything else.
+  const int64_t h = choose_split(r, s2, true);
+  if (use_side && h > 0 && s2 >= r.far_min) {
+    CAP_TRY(gemm_tn(ctx, r.M, h, h, s1, -1.0, R12, ldr, R12, ldr, 1.0, W22, ldw, CAPITAL_GEMM_C_UPPER));
+    CAP_TRY(gemm_tn(ctx, r.S, h, s2 - h, s1, -1.0, R12, ldr, R12 + h * ldr, ldr, 1.0, W22 + h * ldw, ldw, 0));
+    CAP_TRY(gemm_tn(ctx, r.S, s2 - h, s2 - h, s1, -1.0, R12 + h * ldr, ldr, R12 + h * ldr, ldr, 1.0, W22 + h * ldw + h, ldw,
+                    CAPITAL_GEMM_C_UPPER));
+    CAP_TRY(new_event(ctx, &e_far));
+    CAP_CUDA(cudaEventRecord(e_far, r.S));
+  } else {
+    CAP_TRY(gemm_tn(ctx, r.M, s2, s2, s1, -1.0, R12, ldr, R12, ldr, 1.0, W22, ldw, CAPITAL_GEMM_C_UPPER));
+  }
   if (complete) {
-    // inverse combine (cholinv.hpp:147-155): Rinv12 = -Rinv11 R12 Rinv22
-    //   T^T = R12^T Rinv11^T      (B = RiT11, lower triangular)
-    CAP_TRY(gemm_tn(ctx, st, s2, s1, s1, 1.0, R12, ldr, RiT, ldrit, 0.0, W21, ldw, CAPITAL_GEMM_B_LOWER));
-    //   Rinv12 = -(T^T)^T Rinv22  (B = Ri22, upper triangular)
-    CAP_TRY(gemm_tn(ctx, st, s1, s2, s2, -1.0, W21, ldw, Ri22, ldri, 0.0, Ri12, ldri, CAPITAL_GEMM_B_UPPER));
-    CAP_TRY(transpose_block(ctx, st, s1, s2, Ri12, ldri, RiT21, ldrit, 1.0));
+    // inverse combine, first half (cholinv.hpp:151): T^T = R12^T Rinv11^T  (B = RiT11, lower triangular) -- nobody needs
+    // it before the right child is done, so it goes to the deferred stream.
+    CAP_TRY(gemm_tn(ctx, tS, s2, s1, s1, 1.0, R12, ldr, RiT, ldrit, 0.0, W21, ldw, CAPITAL_GEMM_B_LOWER));
+    if (use_side) {
+      CAP_TRY(new_event(ctx, &e_tt));
+      CAP_CUDA(cudaEventRecord(e_tt, r.S));
+    }
+  }
+  CAP_TRY(rec(r, o + s1, s2, true, e_far, depth + 1));
+  if (complete) {
+    if (e_tt) CAP_CUDA(cudaStreamWaitEvent(r.M, e_tt, 0));
+    //   Rinv12 = -(T^T)^T Rinv22  (B = Ri22, upper triangular)   (cholinv.hpp:152-155)
+    CAP_TRY(gemm_tn(ctx, r.M, s1, s2, s2, -1.0, W21, ldw, Ri22, ldri, 0.0, Ri12, ldri, CAPITAL_GEMM_B_UPPER));
+    CAP_TRY(transpose_block(ctx, r.M, s1, s2, Ri12, ldri, RiT21, ldrit, 1.0));
   }
   return CAPITAL_OK;
 }
@@ -62,6 +133,30 @@ capital_status_t rec(capital_ctx* ctx, cudaStream_t st, int64_t n, double* W, in
 }  // namespace
 
 capital_status_t cholinv_local(capital_ctx* ctx, cudaStream_t st, int64_t n, double* W, int64_t ldw, double* R, int64_t ldr, double* Ri,
-                               int64_t ldri, double* RiT, int64_t ldrit, bool complete_top, int64_t bc, int split) {
-  return rec(ctx, st, n, W, ldw, R, ldr, Ri, ldri, RiT, ldrit, complete_top, bc, split);
+                               int64_t ldri, double* RiT, int64_t ldrit, bool complete_top, int64_t bc, int split,
+                               const CholinvHooks* hooks) {
+  // `st` is the caller-visible stream; the recursion runs on the context's high-priority stream, fenced by events.
+  cudaStream_t M = ctx->hi ? ctx->hi : st;
+  cudaStream_t S = (ctx->hi && ctx->side && n >= 1024) ? ctx->side : nullptr;
+  ctx->dep_used = 0;
+  cudaEvent_t e_in = nullptr, e_out = nullptr, e_s = nullptr;
+  if (M != st) {
+    CAP_TRY(new_event(ctx, &e_in));
+    CAP_CUDA(cudaEventRecord(e_in, st));
+    CAP_CUDA(cudaStreamWaitEvent(M, e_in, 0));
+    if (S) CAP_CUDA(cudaStreamWaitEvent(S, e_in, 0));
+  }
+  Rec r{ctx, M, S, W, R, Ri, RiT, ldw, ldr, ldri, ldrit, bc, split, hooks, 2048};
+  CAP_TRY(rec(r, 0, n, complete_top, nullptr, 0));
+  if (M != st) {
+    if (S) {  // join the deferred stream (all its work has been consumed through events, this is just the fence)
+      CAP_TRY(new_event(ctx, &e_s));
+      CAP_CUDA(cudaEventRecord(e_s, S));
+      CAP_CUDA(cudaStreamWaitEvent(M, e_s, 0));
+    }
+    CAP_TRY(new_event(ctx, &e_out));
+    CAP_CUDA(cudaEventRecord(e_out, M));
+    CAP_CUDA(cudaStreamWaitEvent(st, e_out, 0));
+  }
+  return CAPITAL_OK;
 }

@@ -41,7 +41,13 @@ struct capital_ctx {
   int device = 0;
   int num_sms = 148;
   cudaStream_t stream = nullptr;   // main stream (caller's or owned)
-  cudaStream_t side = nullptr;     // side stream for off-critical-path products
+  cudaStream_t side = nullptr;     // low-priority stream: deferred ("far") trailing updates, T^T products
+  cudaStream_t hi = nullptr;       // high-priority stream: the critical chain of the recursion
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;  // H2D / D2H streams of the host-pointer path
+  std::vector<cudaEvent_t> dep_pool;  // dependency events (timing disabled), recycled per factor call
+  size_t dep_used = 0;
+  std::vector<cudaEvent_t> io_pool;   // events of the host-pointer streaming path
+  size_t io_used = 0;
   bool own_stream = false;
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_fork = nullptr, ev_join = nullptr;
   cuTensorMapEncodeTiled_fn encode = nullptr;
@@ -96,7 +102,7 @@ capital_status_t copy_block(capital_ctx* ctx, cudaStream_t st, int64_t rows, int
                             double* dst, int64_t ldd);
 capital_status_t zero_block(capital_ctx* ctx, cudaStream_t st, int64_t rows, int64_t cols, double* dst, int64_t ldd);
 capital_status_t pack_upper(capital_ctx* ctx, cudaStream_t st, int64_t n, const double* src, int64_t lds, double* packed,
-                            int zero_diag);
+                            int zero_diag, int64_t col_begin = 0, int64_t col_end = -1);
 capital_status_t unpack_upper(capital_ctx* ctx, cudaStream_t st, int64_t n, const double* packed, double* dst, int64_t ldd);
 capital_status_t triu_copy(capital_ctx* ctx, cudaStream_t st, int64_t n, const double* src, int64_t lds, double* dst,
                            int64_t ldd, int zero_diag);
@@ -120,8 +126,17 @@ capital_status_t leaf_cholinv(capital_ctx* ctx, cudaStream_t st, int nb, const d
 
 // ---- cholinv.cu -------------------------------------------------------------------------------
 // local (single-GPU) recursive CholInv on dense n x n blocks; W is destroyed (Schur complements).
+// Optional callbacks of the top-level call (host-pointer path): `need_cols` makes `st` wait until columns [0, col_end)
+// of W have arrived from the host; `left_done` fires once, after the top-level left child, when columns [0, s1) of R
+// and Rinv are final.
+struct CholinvHooks {
+  void* user;
+  capital_status_t (*need_cols)(void* user, cudaStream_t st, int64_t col_end);
+  capital_status_t (*left_done)(void* user, cudaStream_t st, int64_t s1);
+};
 capital_status_t cholinv_local(capital_ctx* ctx, cudaStream_t st, int64_t n, double* W, int64_t ldw, double* R, int64_t ldr,
-                               double* Ri, int64_t ldri, double* RiT, int64_t ldrit, bool complete_top, int64_t bc, int split);
+                               double* Ri, int64_t ldri, double* RiT, int64_t ldrit, bool complete_top, int64_t bc, int split,
+                               const CholinvHooks* hooks = nullptr);
 
 static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

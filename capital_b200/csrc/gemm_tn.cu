@@ -75,8 +75,12 @@ __global__ void __launch_bounds__(((BM / WM) * (BN / WN) + 4) * 32, MINB)
   constexpr int FM = WM / 8, FN = WN / 8;
   constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
 
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int flags = p.flags;
+  // Longest-tile-first: with a triangular operand the k extent grows with the tile index, so launch order is reversed
+  // to put the long tiles in the first wave and the short ones in the tail.
+  const int tm = (flags & CAPITAL_GEMM_A_UPPER) ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+  const int tn = (flags & CAPITAL_GEMM_B_UPPER) ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+  const int m0 = tm * BM, n0 = tn * BN;
   if ((flags & CAPITAL_GEMM_C_UPPER) && m0 > n0 + BN - 1) return;  // tile strictly below the diagonal
 
   int kb = 0, ke = p.K;

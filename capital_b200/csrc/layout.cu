@@ -43,9 +43,9 @@ __global__ void zero_kernel(long long rows, long long cols, double* __restrict__
 }
 
 // one block per column chunk: column i of the packed triangle is contiguous (i+1 entries at i(i+1)/2)
-__global__ void pack_upper_kernel(long long n, const double* __restrict__ src, long long lds, double* __restrict__ packed,
+__global__ void pack_upper_kernel(long long c0, long long n, const double* __restrict__ src, long long lds, double* __restrict__ packed,
                                   int zero_diag) {
-  for (long long i = blockIdx.x; i < n; i += gridDim.x) {
+  for (long long i = c0 + blockIdx.x; i < n; i += gridDim.x) {
     const double* s = src + i * lds;
     double* d = packed + i * (i + 1) / 2;
     for (long long j = threadIdx.x; j <= i; j += blockDim.x) d[j] = (zero_diag && j == i) ? 0.0 : s[j];
@@ -192,9 +192,12 @@ capital_status_t zero_block(capital_ctx* ctx, cudaStream_t st, int64_t rows, int
   LAUNCH_CHECK();
   return CAPITAL_OK;
 }
-capital_status_t pack_upper(capital_ctx* ctx, cudaStream_t st, int64_t n, const double* src, int64_t lds, double* packed, int zero_diag) {
-  if (n <= 0) return CAPITAL_OK;
-  pack_upper_kernel<<<(int)(n < ctx->num_sms * 8 ? n : ctx->num_sms * 8), 256, 0, st>>>(n, src, lds, packed, zero_diag);
+capital_status_t pack_upper(capital_ctx* ctx, cudaStream_t st, int64_t n, const double* src, int64_t lds, double* packed, int zero_diag,
+                            int64_t col_begin, int64_t col_end) {
+  if (col_end < 0) col_end = n;
+  const int64_t cols = col_end - col_begin;
+  if (cols <= 0) return CAPITAL_OK;
+  pack_upper_kernel<<<(int)(cols < ctx->num_sms * 8 ? cols : ctx->num_sms * 8), 256, 0, st>>>(col_begin, col_end, src, lds, packed, zero_diag);
   LAUNCH_CHECK();
   return CAPITAL_OK;
 }

@@ -14,6 +14,7 @@
 // rsqrt per pivot instead of a sqrt and a divide.
 #include "common.cuh"
 #include <cooperative_groups.h>
+#include <stdlib.h>
 namespace cg = cooperative_groups;
 
 namespace {
@@ -182,7 +183,7 @@ __device__ __forceinline__ void acc_zero(double (&acc)[4][2][2]) {
 // W (nb x nb, upper read, destroyed) -> R, Ri, RiT blocks (full nb x nb blocks written: zeros in the other triangle).
 __global__ void __cluster_dims__(BC_CLUSTER, 1, 1) __launch_bounds__(256, 1)
     basecase_kernel(int nb, double* __restrict__ W, long long ldw, double* __restrict__ R, long long ldr, double* __restrict__ Ri,
-                    long long ldri, double* __restrict__ RiT, long long ldrit, int* __restrict__ info) {
+                    long long ldri, double* __restrict__ RiT, long long ldrit, int* __restrict__ info, long long* __restrict__ dbg) {
   extern __shared__ double sm[];
   double* sA = sm;                     // tile / leaf array a
   double* sB = sm + TILE_DOUBLES;      // tile / leaf array r
@@ -192,6 +193,9 @@ __global__ void __cluster_dims__(BC_CLUSTER, 1, 1) __launch_bounds__(256, 1)
   const int T = nb >> 6;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
   double acc[4][2][2];
+  int dbgi = 0;
+#define DBG_STAMP() do { if (dbg && rank == 0 && threadIdx.x == 0) dbg[dbgi++] = clock64(); } while (0)
+  DBG_STAMP();
 
   // ---------------- Cholesky: right-looking over 64-wide block columns ----------------
   for (int jb = 0; jb < T; jb++) {
@@ -202,8 +206,10 @@ __global__ void __cluster_dims__(BC_CLUSTER, 1, 1) __launch_bounds__(256, 1)
       leaf_factor_invert(64, sA, sB, sT, info, jb * 64);
       leaf_store(64, sA, sB, R + o + o * ldr, ldr, Ri + o + o * ldri, ldri, RiT + o + o * ldrit, ldrit);
     }
+    if (jb == 0) DBG_STAMP();
     __threadfence();
     cluster.sync();
+    if (jb == 0) DBG_STAMP();
     // row panel: R(jb, j) = Rinv_jj^T W(jb, j), j > jb
     int work = 0;
     for (int j = jb + 1; j < T; j++, work++) {
@@ -222,8 +228,10 @@ __global__ void __cluster_dims__(BC_CLUSTER, 1, 1) __launch_bounds__(256, 1)
 #pragma unroll
           for (int e = 0; e < 2; e++) out[TILE_ROW(i) + (long long)TILE_COL(jj, e) * ldr] = acc[i][jj][e];
     }
+    if (jb == 0) DBG_STAMP();
     __threadfence();
     cluster.sync();
+    if (jb == 0) DBG_STAMP();
     // trailing update: W(i, j) -= R(jb, i)^T R(jb, j), jb < i <= j
     work = 0;
     for (int j = jb + 1; j < T; j++)
@@ -246,9 +254,12 @@ __global__ void __cluster_dims__(BC_CLUSTER, 1, 1) __launch_bounds__(256, 1)
               *p = __ldcg(p) - acc[ii][jj][e];
             }
       }
+    if (jb == 0) DBG_STAMP();
     __threadfence();
     cluster.sync();
+    if (jb == 0) DBG_STAMP();
   }
+  DBG_STAMP();
   // zero the strictly-lower blocks of R (the leaf wrote the diagonal blocks completely)
   {
     int work = 0;
@@ -299,6 +310,7 @@ __global__ void __cluster_dims__(BC_CLUSTER, 1, 1) __launch_bounds__(256, 1)
     __threadfence();
     cluster.sync();
   }
+  DBG_STAMP();
 }
 }  // namespace
 
@@ -329,7 +341,19 @@ capital_status_t basecase_cholinv(capital_ctx* ctx, cudaStream_t st, int nb, dou
     CAP_CUDA(cudaFuncSetAttribute(basecase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  basecase_kernel<<<BC_CLUSTER, 256, smem, st>>>(nb, W, ldw, R, ldr, Ri, ldri, RiT, ldrit, ctx->d_info);
+  long long* dbg = nullptr;
+  if (getenv("CAPITAL_BC_DEBUG")) {
+    CAP_TRY(ctx->workspace("bc_dbg", 64 * sizeof(long long), (void**)&dbg));
+    CAP_CUDA(cudaMemsetAsync(dbg, 0, 64 * sizeof(long long), st));
+  }
+  basecase_kernel<<<BC_CLUSTER, 256, smem, st>>>(nb, W, ldw, R, ldr, Ri, ldri, RiT, ldrit, ctx->d_info, dbg);
+  if (dbg) {
+    long long h[16];
+    CAP_CUDA(cudaMemcpyAsync(h, dbg, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CAP_CUDA(cudaStreamSynchronize(st));
+    fprintf(stderr, "[bc nb=%d] leaf0=%lld bar=%lld panel0=%lld bar=%lld trail0=%lld bar=%lld | chol_total=%lld inverse=%lld total=%lld cycles\n", nb,
+            h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5], h[7] - h[0], h[8] - h[7], h[8] - h[0]);
+  }
   ctx->counters.kernel_launches++;
   ctx->counters.leaf_launches++;
   CAP_CUDA(cudaGetLastError());
