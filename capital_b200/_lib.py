@@ -14,7 +14,7 @@ GEMM_A_UPPER, GEMM_A_LOWER, GEMM_B_UPPER, GEMM_B_LOWER, GEMM_C_UPPER = 1, 2, 4, 
 EXPORTS = [  # every symbol include/capital_b200.h declares
     "capital_grid_square", "capital_grid_rect", "capital_cholinv_bc_dimension", "capital_create",
     "capital_comm_unique_id", "capital_comm_init", "capital_destroy", "capital_last_error", "capital_get_counters",
-    "capital_reset_counters", "capital_synchronize", "capital_last_factor_ms", "capital_profile_begin", "capital_profile_end", "capital_distribute_symmetric_f64",
+    "capital_reset_counters", "capital_synchronize", "capital_last_factor_ms", "capital_profile_begin", "capital_profile_end", "capital_set_overlap", "capital_distribute_symmetric_f64",
     "capital_distribute_random_f64", "capital_cholinv_factor_f64", "capital_cholinv_residual_f64",
     "capital_cacqr_factor_f64", "capital_cacqr_residual_f64", "capital_blas_gemm_tn_f64",
     "capital_lapack_potrf_trtri_f64",
@@ -67,6 +67,7 @@ def lib() -> C.CDLL:
     L.capital_synchronize.argtypes = [vp]
     L.capital_last_factor_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.capital_profile_begin.argtypes = [vp]
+    L.capital_set_overlap.argtypes = [vp, ci]
     L.capital_profile_end.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(i64)]
     L.capital_distribute_symmetric_f64.argtypes = [vp, vp, i64, ci]
     L.capital_distribute_random_f64.argtypes = [vp, vp, i64, i64, i64]
@@ -117,6 +118,9 @@ class Context:
         ms = C.c_float()
         self.check(lib().capital_last_factor_ms(self._h, C.byref(ms)))
         return float(ms.value)
+
+    def set_overlap(self, enabled: bool):
+        self.check(lib().capital_set_overlap(self._h, int(enabled)))
 
     def profile_begin(self):
         self.check(lib().capital_profile_begin(self._h))

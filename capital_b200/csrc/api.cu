@@ -233,6 +233,11 @@ capital_status_t capital_last_factor_ms(const capital_ctx* ctx_, float* ms) {
   return CAPITAL_OK;
 }
 
+capital_status_t capital_set_overlap(capital_ctx* ctx, int enabled) {
+  if (!ctx) return CAPITAL_ERR_INVALID;
+  ctx->no_overlap = !enabled;
+  return CAPITAL_OK;
+}
 capital_status_t capital_profile_begin(capital_ctx* ctx) {
   if (!ctx) return CAPITAL_ERR_INVALID;
   ctx->profiling = true; ctx->prof_used = 0; ctx->prof_recs.clear();

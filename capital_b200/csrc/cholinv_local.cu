@@ -36,16 +36,17 @@ struct Rec {
   int split;
   const CholinvHooks* hooks;
   int64_t far_min;  // trailing updates smaller than this are not split
+  bool base_aligned;  // all four buffers 16-byte aligned with even leading dimensions (cluster kernel uses 16-byte accesses)
 };
 
 // Levels above the base case (n > bc) split by the reference's rule s1 = n >> split (cholinv.hpp:92,107); it fixes
 // which Rinv block stays zero when complete_inv == 0.  Below it -- the reference's potrf/trtri base case
 // (cholinv.hpp:93-104) -- the recursion continues with 64-aligned halves down to the cluster / leaf kernels.
 // Returns 0 when the block is handled by a single kernel.
-int64_t choose_split(const Rec& r, int64_t n, bool complete) {
+int64_t choose_split(const Rec& r, int64_t o, int64_t n, bool complete) {
   if (n > r.bc && (n >> r.split) >= r.split && (n >> r.split) > 0 && (n > LEAF_MAX || !complete)) return n >> r.split;
   if (n <= LEAF_MAX) return 0;
-  if (n <= BASECASE_MAX && n % 64 == 0 && complete) return 0;
+  if (n <= BASECASE_MAX && n % 64 == 0 && complete && r.base_aligned && (o & 1) == 0) return 0;
   return split_point(n);
 }
 
@@ -68,7 +69,7 @@ capital_status_t rec(Rec& r, int64_t o, int64_t n, bool complete, cudaEvent_t pe
   double* Ri = r.Ri + o * r.ldri + o;
   double* RiT = r.RiT + o * r.ldrit + o;
   const int64_t ldw = r.ldw, ldr = r.ldr, ldri = r.ldri, ldrit = r.ldrit;
-  const int64_t s1 = choose_split(r, n, complete);
+  const int64_t s1 = choose_split(r, o, n, complete);
   if (s1 == 0) {
     if (r.hooks && r.hooks->need_cols) CAP_TRY(r.hooks->need_cols(r.hooks->user, r.M, o + n));
     if (pending) CAP_CUDA(cudaStreamWaitEvent(r.M, pending, 0));
@@ -100,7 +101,7 @@ capital_status_t rec(Rec& r, int64_t o, int64_t n, bool complete, cudaEvent_t pe
   cudaStream_t tS = use_side ? r.S : r.M;
   // trailing update (cholinv.hpp:131-134): A22 -= R12^T R12, upper tiles only.
   // near = what the right child's left subtree reads (leading h x h block), far = everything else.
-  const int64_t h = choose_split(r, s2, true);
+  const int64_t h = choose_split(r, o + s1, s2, true);
   if (use_side && h > 0 && s2 >= r.far_min) {
     CAP_TRY(gemm_tn(ctx, r.M, h, h, s1, -1.0, R12, ldr, R12, ldr, 1.0, W22, ldw, CAPITAL_GEMM_C_UPPER));
     CAP_TRY(gemm_tn(ctx, r.S, h, s2 - h, s1, -1.0, R12, ldr, R12 + h * ldr, ldr, 1.0, W22 + h * ldw, ldw, 0));
@@ -137,7 +138,7 @@ capital_status_t cholinv_local(capital_ctx* ctx, cudaStream_t st, int64_t n, dou
                                const CholinvHooks* hooks) {
   // `st` is the caller-visible stream; the recursion runs on the context's high-priority stream, fenced by events.
   cudaStream_t M = ctx->hi ? ctx->hi : st;
-  cudaStream_t S = (ctx->hi && ctx->side && n >= 1024) ? ctx->side : nullptr;
+  cudaStream_t S = (ctx->hi && ctx->side && n >= 1024 && !ctx->no_overlap) ? ctx->side : nullptr;
   ctx->dep_used = 0;
   cudaEvent_t e_in = nullptr, e_out = nullptr, e_s = nullptr;
   if (M != st) {
@@ -146,7 +147,8 @@ capital_status_t cholinv_local(capital_ctx* ctx, cudaStream_t st, int64_t n, dou
     CAP_CUDA(cudaStreamWaitEvent(M, e_in, 0));
     if (S) CAP_CUDA(cudaStreamWaitEvent(S, e_in, 0));
   }
-  Rec r{ctx, M, S, W, R, Ri, RiT, ldw, ldr, ldri, ldrit, bc, split, hooks, 2048};
+  const bool aligned = ((((uintptr_t)W | (uintptr_t)R | (uintptr_t)Ri | (uintptr_t)RiT) & 15) == 0) && !((ldw | ldr | ldri | ldrit) & 1);
+  Rec r{ctx, M, S, W, R, Ri, RiT, ldw, ldr, ldri, ldrit, bc, split, hooks, 2048, aligned};
   CAP_TRY(rec(r, 0, n, complete_top, nullptr, 0));
   if (M != st) {
     if (S) {  // join the deferred stream (all its work has been consumed through events, this is just the fence)

@@ -70,6 +70,7 @@ struct capital_ctx {
   // per-launch timing of the dominant kernel (gemm_tn 128x128), off by default
   struct ProfRec { cudaEvent_t e0, e1; double flops; };
   bool profiling = false;
+  bool no_overlap = false;  // debug / measurement: run the recursion on one stream
   std::vector<cudaEvent_t> prof_pool;
   size_t prof_used = 0;
   std::vector<ProfRec> prof_recs;

@@ -145,41 +145,56 @@ capital_status_t product(Dist& D, int64_t m, int64_t n, int64_t k, double alpha,
                          int64_t ldy, double beta, double* C, int64_t ldc, int flags) {
   capital_ctx* ctx = D.ctx;
   const capital_grid_t& g = D.g;
-  const int d = g.d, me = g.rank;
-  const int64_t ldk = packed_ld(k);
-  const int srcX = rank_of(g, g.y, g.z, g.z);  // owner of X rows = z, cols = y
-  const int srcY = rank_of(g, g.x, g.z, g.z);  // owner of Y rows = z, cols = x
-  const bool iAmXsrc = (g.y == g.z);           // my block (cols x, rows y=z) is needed by row y' = x of my layer
-  const bool iAmYsrc = (g.y == g.z);           // my block is needed by column x of my layer
-  const double* Xuse = X; int64_t ldxu = ldx;
-  const double* Yuse = Y; int64_t ldyu = ldy;
-  // stage outgoing blocks contiguously
-  double* sendX = D.bufS;
-  double* sendY = D.bufS + ldk * (m > n ? m : n);
-  bool needSendX = false, needSendY = false;
-  if (iAmXsrc) for (int xx = 0; xx < d; xx++) if (rank_of(g, xx, g.x, g.z) != me) needSendX = true;
-  if (iAmYsrc) for (int yy = 0; yy < d; yy++) if (rank_of(g, g.x, yy, g.z) != me) needSendY = true;
-  if (needSendX) CAP_TRY(copy_block(ctx, D.st, k, m, X, ldx, sendX, ldk));
-  if (needSendY) CAP_TRY(copy_block(ctx, D.st, k, n, Y, ldy, sendY, ldk));
-  CAP_NCCL(nccl().GroupStart());
-  if (iAmXsrc)  // destinations: all (xx, y' = my x, z)
-    for (int xx = 0; xx < d; xx++) {
-      const int dst = rank_of(g, xx, g.x, g.z);
-      if (dst != me) CAP_NCCL(nccl().Send(sendX, (size_t)ldk * m, ncclFloat64, dst, D.world, D.st));
-    }
-  if (iAmYsrc)  // destinations: all (x' = my x, yy, z)
-    for (int yy = 0; yy < d; yy++) {
-      const int dst = rank_of(g, g.x, yy, g.z);
-      if (dst != me) CAP_NCCL(nccl().Send(sendY, (size_t)ldk * n, ncclFloat64, dst, D.world, D.st));
-    }
-  if (srcX != me) { CAP_NCCL(nccl().Recv(D.bufX, (size_t)ldk * m, ncclFloat64, srcX, D.world, D.st)); Xuse = D.bufX; ldxu = ldk; }
-  if (srcY != me) { CAP_NCCL(nccl().Recv(D.bufY, (size_t)ldk * n, ncclFloat64, srcY, D.world, D.st)); Yuse = D.bufY; ldyu = ldk; }
-  CAP_NCCL(nccl().GroupEnd());
-  // local product on the k = z slice
+  const int d = g.d, c = g.c, me = g.rank;
+  // The contraction index splits into d owner classes (k mod d = kb); the c layers share them: layer z takes the classes
+  // kb = z (mod c) when c <= d (the reference has c == d: exactly one class per layer, summa.hpp:185-193), and when
+  // c > d (2 x 1 x 1) the single class is cut into c/d row chunks of the local window.
+  const int nslices = c > d ? c : d;
+  const int nchunk = c > d ? c / d : 1;
   const int64_t ldp = packed_ld(m);
+  bool first = true;
   if (flags & CAPITAL_GEMM_C_UPPER) CAP_CUDA(cudaMemsetAsync(D.bufP, 0, (size_t)ldp * n * 8, D.st));
-  CAP_TRY(gemm_tn(ctx, D.st, m, n, k, alpha, Xuse, ldxu, Yuse, ldyu, 0.0, D.bufP, ldp, flags));
-  if (g.c > 1) CAP_NCCL(nccl().AllReduce(D.bufP, D.bufP, (size_t)ldp * n, ncclFloat64, ncclSum, D.depth, D.st));
+  for (int sl = g.z % (c < nslices ? c : nslices); sl < nslices; sl += c) {
+    const int kb = sl % d, chunk = sl / d;
+    int64_t r0 = 0, r1 = k;
+    int fl = flags;
+    if (nchunk > 1) {
+      r0 = (k * chunk / nchunk) & ~(int64_t)1;
+      r1 = chunk + 1 == nchunk ? k : ((k * (chunk + 1) / nchunk) & ~(int64_t)1);
+      fl &= CAPITAL_GEMM_C_UPPER;  // a row chunk is not aligned with the operand's diagonal any more
+    }
+    const int64_t kk = r1 - r0;
+    if (kk <= 0) continue;
+    const int64_t ldk = packed_ld(kk);
+    const int srcX = rank_of(g, g.y, kb, g.z);  // owner of X rows = kb, cols = y
+    const int srcY = rank_of(g, g.x, kb, g.z);  // owner of Y rows = kb, cols = x
+    const bool iAmSrc = (g.y == kb);            // my block is the X block of row y' = x and the Y block of column x
+    const double* Xuse = X + r0; int64_t ldxu = ldx;
+    const double* Yuse = Y + r0; int64_t ldyu = ldy;
+    double* sendX = D.bufS;
+    double* sendY = D.bufS + ldk * (m > n ? m : n);
+    bool needSendX = false, needSendY = false;
+    if (iAmSrc) for (int xx = 0; xx < d; xx++) if (rank_of(g, xx, g.x, g.z) != me) needSendX = true;
+    if (iAmSrc) for (int yy = 0; yy < d; yy++) if (rank_of(g, g.x, yy, g.z) != me) needSendY = true;
+    if (needSendX) CAP_TRY(copy_block(ctx, D.st, kk, m, X + r0, ldx, sendX, ldk));
+    if (needSendY) CAP_TRY(copy_block(ctx, D.st, kk, n, Y + r0, ldy, sendY, ldk));
+    if (needSendX || needSendY || srcX != me || srcY != me) {
+      CAP_NCCL(nccl().GroupStart());
+      if (iAmSrc)  // X destinations: all (xx, y' = my x, z);  Y destinations: all (x' = my x, yy, z)
+        for (int t = 0; t < d; t++) {
+          const int dx = rank_of(g, t, g.x, g.z), dy = rank_of(g, g.x, t, g.z);
+          if (dx != me) CAP_NCCL(nccl().Send(sendX, (size_t)ldk * m, ncclFloat64, dx, D.world, D.st));
+          if (dy != me) CAP_NCCL(nccl().Send(sendY, (size_t)ldk * n, ncclFloat64, dy, D.world, D.st));
+        }
+      if (srcX != me) { CAP_NCCL(nccl().Recv(D.bufX, (size_t)ldk * m, ncclFloat64, srcX, D.world, D.st)); Xuse = D.bufX; ldxu = ldk; }
+      if (srcY != me) { CAP_NCCL(nccl().Recv(D.bufY, (size_t)ldk * n, ncclFloat64, srcY, D.world, D.st)); Yuse = D.bufY; ldyu = ldk; }
+      CAP_NCCL(nccl().GroupEnd());
+    }
+    CAP_TRY(gemm_tn(ctx, D.st, m, n, kk, alpha, Xuse, ldxu, Yuse, ldyu, first ? 0.0 : 1.0, D.bufP, ldp, fl));
+    first = false;
+  }
+  if (first) CAP_CUDA(cudaMemsetAsync(D.bufP, 0, (size_t)ldp * n * 8, D.st));  // this layer had no slice
+  if (c > 1) CAP_NCCL(nccl().AllReduce(D.bufP, D.bufP, (size_t)ldp * n, ncclFloat64, ncclSum, D.depth, D.st));
   axpby_kernel<<<grid_for(ctx, m * n), 256, 0, D.st>>>(m, n, D.bufP, ldp, beta, C, ldc, (flags & CAPITAL_GEMM_C_UPPER) ? 1 : 0);
   ctx->counters.kernel_launches++;
   CAP_CUDA(cudaGetLastError());
@@ -315,8 +330,9 @@ capital_status_t dist_cholinv_factor(capital_ctx* ctx, const double* A_local, in
                                      capital_structure_t ostruct, double* R_local, double* Rinv_local) {
   const capital_grid_t& g = ctx->grid;
   CAP_TRY(need_comm(ctx));
-  if (g.c != g.d || n % g.d != 0) {
-    ctx->set_error("distributed cholinv needs the reference's cubic grid (c == d, summa.hpp:16-31) and d | n");
+  // the reference requires c == d (summa.hpp:16-31); c | d and d | c grids (2x1x1, 1x2x2) are this library's extension
+  if ((g.c % g.d != 0 && g.d % g.c != 0) || n % g.d != 0) {
+    ctx->set_error("distributed cholinv needs a grid with c | d or d | c, and d | n");
     return CAPITAL_ERR_UNSUPPORTED;
   }
   const int64_t L = n / g.d, ld = round_up(L, 16);
@@ -365,7 +381,7 @@ capital_status_t dist_cholinv_residual(capital_ctx* ctx, const double* A_local, 
                                        const double* R_local, double* residual) {
   const capital_grid_t& g = ctx->grid;
   CAP_TRY(need_comm(ctx));
-  if (g.c != g.d || n % g.d != 0) return CAPITAL_ERR_UNSUPPORTED;
+  if ((g.c % g.d != 0 && g.d % g.c != 0) || n % g.d != 0) return CAPITAL_ERR_UNSUPPORTED;
   const int64_t L = n / g.d, ld = round_up(L, 16);
   cudaStream_t st = ctx->stream;
   const size_t r_count = structure == CAPITAL_UPPERTRI_PACKED ? (size_t)L * (L + 1) / 2 : (size_t)L * L;

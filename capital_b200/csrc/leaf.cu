@@ -24,6 +24,17 @@ constexpr int TLD = 68;            // DMMA tiles: rows of 64 k-contiguous double
 constexpr int TILE_DOUBLES = 64 * TLD;
 constexpr int BC_CLUSTER = 8;
 
+// 1/sqrt(d) off the critical path's slow library routine: FP32 seed + two FP64 Newton steps (relative error ~1e-16 for
+// d inside the FP32 range; outside it the library routine is used)
+__device__ __forceinline__ double fast_rsqrt(double d) {
+  if (!(d > 1e-30 && d < 1e30)) return rsqrt(d);
+  double y = (double)rsqrtf((float)d);
+  const double h = 0.5 * d;
+  y = y * (1.5 - h * y * y);
+  y = y * (1.5 - h * y * y);
+  return y;
+}
+
 // ---- leaf: factor + invert an nb x nb block held in shared memory ---------------------------------------------
 // a : in  upper triangle of the SPD block (destroyed), out R^{-1} (upper, zeros below)
 // r : out R (upper, zeros below)
@@ -141,23 +152,22 @@ __global__ void __launch_bounds__(256, 1)
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
-// copy a 64 (k) x 64 (cols) global block (k contiguous) into a padded tile: dst[col * TLD + k]
+// copy a 64 (k) x 64 (cols) global block (k contiguous, 16-byte aligned, even ld) into a padded tile: dst[col * TLD + k]
 __device__ __forceinline__ void tile_load(double* __restrict__ dst, const double* __restrict__ src, long long ld) {
-  const int k = threadIdx.x & 63, c0 = threadIdx.x >> 6;
+  const int k2 = (threadIdx.x & 31) * 2, c0 = threadIdx.x >> 5;
+  double2 v[8];
 #pragma unroll
-  for (int r = 0; r < 16; r++) {
-    const int c = c0 + 4 * r;
-    dst[c * TLD + k] = __ldcg(src + k + (long long)c * ld);
-  }
+  for (int r = 0; r < 8; r++) v[r] = __ldcg(reinterpret_cast<const double2*>(src + k2 + (long long)(c0 + 8 * r) * ld));
+#pragma unroll
+  for (int r = 0; r < 8; r++) *reinterpret_cast<double2*>(dst + (c0 + 8 * r) * TLD + k2) = v[r];
 }
 // acc += As^T Bs for the 64x64 tile; warp w owns rows (w&1)*32.., cols (w>>1)*16..; As/Bs: [row][k] padded tiles.
-// kmax: contraction length actually needed (multiple of 4, <= 64)
-__device__ __forceinline__ void tile_mma(double (&acc)[4][2][2], const double* __restrict__ As, const double* __restrict__ Bs, int kmax) {
+__device__ __forceinline__ void tile_mma(double (&acc)[4][2][2], const double* __restrict__ As, const double* __restrict__ Bs) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
   const double* ap = As + ((w & 1) * 32 + g) * TLD + q;
   const double* bp = Bs + ((w >> 1) * 16 + g) * TLD + q;
 #pragma unroll 4
-  for (int k0 = 0; k0 < kmax; k0 += 4) {
+  for (int k0 = 0; k0 < 64; k0 += 4) {
     double af[4], bf[2];
 #pragma unroll
     for (int i = 0; i < 4; i++) af[i] = ap[i * 8 * TLD + k0];
@@ -175,41 +185,254 @@ __device__ __forceinline__ void acc_zero(double (&acc)[4][2][2]) {
 #pragma unroll
     for (int j = 0; j < 2; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 }
-// element (row, col) of the tile owned by this lane for fragment (i, j), value e
 #define TILE_ROW(i) ((w & 1) * 32 + (i) * 8 + g)
 #define TILE_COL(j, e) ((w >> 1) * 16 + (j) * 8 + 2 * q + (e))
+// accumulators -> shared tile in [col][row] order (row contiguous), scaled
+__device__ __forceinline__ void acc_to_smem_colmajor(const double (&acc)[4][2][2], double* __restrict__ sC, double scale) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) sC[TILE_COL(j, e) * TLD + TILE_ROW(i)] = scale * acc[i][j][e];
+}
+// accumulators -> shared tile in [row][col] order (used as the next A operand: rows = output rows, k = columns)
+__device__ __forceinline__ void acc_to_smem_rowmajor(const double (&acc)[4][2][2], double* __restrict__ sC, double scale) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) sC[TILE_ROW(i) * TLD + TILE_COL(j, e)] = scale * acc[i][j][e];
+}
+// global(64 x 64 block, column-major) = [beta * global +] sC ([col][row]) with 16-byte coalesced accesses
+template <bool ACCUM>
+__device__ __forceinline__ void tile_store(double* __restrict__ dst, long long ld, const double* __restrict__ sC) {
+  const int r2 = (threadIdx.x & 31) * 2, c0 = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    const int c = c0 + 8 * r;
+    double2 v = *reinterpret_cast<const double2*>(sC + c * TLD + r2);
+    double2* p = reinterpret_cast<double2*>(dst + r2 + (long long)c * ld);
+    if (ACCUM) { const double2 o = __ldcg(p); v.x += o.x; v.y += o.y; }
+    *p = v;
+  }
+}
+// transposed store: global(col-block rows, row-block cols) = sC^T, reading sC ([row][col] order) so that accesses stay coalesced
+__device__ __forceinline__ void tile_store_from_rowmajor(double* __restrict__ dst, long long ld, const double* __restrict__ sCr) {
+  // sCr[row * TLD + col] holds value(row, col); we write dst(col, row) = value(row, col): dst column index = row
+  const int c2 = (threadIdx.x & 31) * 2, r0 = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    const int row = r0 + 8 * r;
+    const double2 v = *reinterpret_cast<const double2*>(sCr + row * TLD + c2);
+    *reinterpret_cast<double2*>(dst + c2 + (long long)row * ld) = v;
+  }
+}
+
+// ---- fast 64 x 64 leaf: two warp-resident 32 x 32 factor+invert steps glued by DMMA products ------------------
+// The pivot chain is the critical path of the whole factorization (16384 dependent pivots at n = 16384).  A block-wide
+// formulation pays two __syncthreads and several shared-memory round trips per pivot (~1200 cycles measured); here
+// a single warp holds a 32 x 32 block in registers (lane j = column j), pivots are broadcast by shuffles, and the
+// reciprocal square root is an FP32 seed + two FP64 Newton steps: ~200 cycles per pivot, no barrier in the chain.
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+// c[i] = A(i, lane) (upper part meaningful) -> R written to sRb (element (i, j) at sRb[j * TLD + i]), x[i] = Rinv(i, lane).
+// ub: 64 doubles of shared scratch (the scaled pivot row is broadcast through it: one conflict-free store and
+// pipelined broadcast loads per pivot instead of 2 x 31 dependent shuffles).  The next pivot's rsqrt is started as
+// soon as its diagonal entry is final, so it overlaps with the rest of the rank-1 update.
+__device__ __forceinline__ void warp_potrf_trtri_32(double (&c)[32], double (&x)[32], double* __restrict__ sRb, double* __restrict__ ub,
+                                                    int lane, int* info, int pivot_base, long long* dbg2) {
+  double myrs = 0.0;
+  if (dbg2 && lane == 0) dbg2[0] = clock64();
+  double d = shfl_d(c[0], 0);
+  if (!(d > 0.0)) { if (lane == 0) atomicCAS(info, 0, pivot_base + 1); d = 1.0; }
+  double rs = fast_rsqrt(d);
+#pragma unroll
+  for (int k = 0; k < 32; k++) {
+    const double u = (lane > k) ? c[k] * rs : (lane == k ? d * rs : 0.0);  // R(k, lane)
+    c[k] = u;
+    if (lane == k) myrs = rs;
+    double* row = ub + (k & 1) * 32;
+    row[lane] = u;
+    __syncwarp();
+    if (k < 31) {
+      c[k + 1] = fma(-row[k + 1], u, c[k + 1]);
+      d = shfl_d(c[k + 1], k + 1);  // next pivot: final already
+      if (!(d > 0.0)) { if (lane == k + 1) atomicCAS(info, 0, pivot_base + k + 2); d = 1.0; }
+      rs = fast_rsqrt(d);
+#pragma unroll
+      for (int i = k + 2; i < 32; i++) c[i] = fma(-row[i], u, c[i]);  // A(i, lane) -= R(k, i) R(k, lane)
+    }
+  }
+  if (dbg2 && lane == 0) dbg2[1] = clock64();
+#pragma unroll
+  for (int i = 0; i < 32; i++) {
+    sRb[lane * TLD + i] = c[i];  // c[i] == 0 below the diagonal by construction (u = 0 for lane < k)
+    x[i] = (i == lane) ? myrs : 0.0;
+  }
+  __syncwarp();
+  // column `lane` of X = R^{-1}: X(i, j) = -rs_i * sum_{t = i+1..j} R(i, t) X(t, j);  R(i, t) read as a broadcast from sRb
+#pragma unroll
+  for (int i = 30; i >= 0; i--) {
+    const double rsi = shfl_d(myrs, i);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+    for (int t = i + 1; t < 32; t++) {  // x[t] == 0 for t > lane
+      const double rit = sRb[t * TLD + i];
+      if ((t & 3) == 0) s0 = fma(rit, x[t], s0);
+      else if ((t & 3) == 1) s1 = fma(rit, x[t], s1);
+      else if ((t & 3) == 2) s2 = fma(rit, x[t], s2);
+      else s3 = fma(rit, x[t], s3);
+    }
+    if (lane > i) x[i] = -rsi * ((s0 + s1) + (s2 + s3));
+  }
+  if (dbg2 && lane == 0) dbg2[2] = clock64();
+}
+
+// acc(8 x 16 per warp) += A^T B over k in [k0, k0 + 32) for the 32 x 32 output block at (rows ar.., cols bc..) of the tiles
+// As ([row][k]) and Bs ([col][k]); warp w owns fragment row (w & 3) and fragment columns 2 (w >> 2) + {0, 1}.
+__device__ __forceinline__ void mma32(double (&acc)[2][2], const double* __restrict__ As, int ar, const double* __restrict__ Bs, int bc, int k0) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
+  const double* ap = As + (ar + (w & 3) * 8 + g) * TLD + k0 + q;
+  const double* bp = Bs + (bc + (w >> 2) * 16 + g) * TLD + k0 + q;
+#pragma unroll
+  for (int k = 0; k < 32; k += 4) {
+    const double a = ap[k], b0 = bp[k], b1 = bp[8 * TLD + k];
+    dmma884(acc[0][0], acc[0][1], a, b0);
+    dmma884(acc[1][0], acc[1][1], a, b1);
+  }
+}
+#define M32_ROW ((w & 3) * 8 + g)
+#define M32_COL(j, e) ((w >> 2) * 16 + (j) * 8 + 2 * q + (e))
+
+// sA: the block, element (row, col) at sA[col * TLD + row] (upper part read).  Outputs as full 64 x 64 tiles:
+//   sR [col][row] = R,   sX [col][row] = Rinv,   sXT [col][row] = Rinv^T   (zeros in the other triangle)
+// sA is destroyed.  All 256 threads must call.
+__device__ void leaf64_fast(double* __restrict__ sA, double* __restrict__ sR, double* __restrict__ sX, double* __restrict__ sXT,
+                            double* __restrict__ ub, int* info, int pivot_base, long long* dbg2 = nullptr) {
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, q = lane & 3;
+  for (int idx = tid; idx < 64 * 64; idx += 256) {
+    const int r = idx & 63, cidx = idx >> 6;
+    sR[cidx * TLD + r] = 0.0; sX[cidx * TLD + r] = 0.0; sXT[cidx * TLD + r] = 0.0;
+  }
+  __syncthreads();
+  double c[32], x[32];
+#pragma unroll 1
+  for (int half = 0; half < 2; half++) {
+    const int o = half * 32;
+    if (half == 1) {
+      // R12 = X11^T A12  (A operand X11: [row i][k] = X11(k, i) = sX[i * TLD + k];  B operand A12: [col][k] = sA[(32 + col) * TLD + k])
+      double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+      mma32(acc, sX, 0, sA, 32, 0);
+#pragma unroll
+      for (int j = 0; j < 2; j++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) sR[(32 + M32_COL(j, e)) * TLD + M32_ROW] = acc[j][e];
+      __syncthreads();
+      // A22 -= R12^T R12
+      double acc2[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+      mma32(acc2, sR + 32 * TLD, 0, sR + 32 * TLD, 0, 0);  // both operands: rows = columns 32.. of sR, k = rows 0..31
+#pragma unroll
+      for (int j = 0; j < 2; j++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) sA[(32 + M32_COL(j, e)) * TLD + 32 + M32_ROW] -= acc2[j][e];
+      __syncthreads();
+    }
+    if (w == 0) {
+#pragma unroll
+      for (int i = 0; i < 32; i++) c[i] = sA[(o + lane) * TLD + o + i];
+      warp_potrf_trtri_32(c, x, sR + o * TLD + o, ub, lane, info, pivot_base + o, (dbg2 && half == 0) ? dbg2 : nullptr);
+      if (dbg2 && half == 0 && lane == 0) dbg2[3] = clock64();
+#pragma unroll
+      for (int i = 0; i < 32; i++) {
+        sX[(o + lane) * TLD + o + i] = x[i];
+        sXT[(o + i) * TLD + o + lane] = x[i];
+      }
+    }
+    __syncthreads();
+  }
+  // X12 = -X11 R12 X22:  T = X11 R12  (A operand [row i][k] = X11(i, k) = sXT[i * TLD + k]; B operand R12: sR[(32 + col) * TLD + k])
+  {
+    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    mma32(acc, sXT, 0, sR, 32, 0);
+    __syncthreads();  // everyone is done reading sA's leftovers; reuse sA rows 0..31 as T in [row][32 + k] order
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) sA[M32_ROW * TLD + 32 + M32_COL(j, e)] = acc[j][e];  // k offset 32 to line up with X22's rows
+    __syncthreads();
+    double acc2[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    mma32(acc2, sA, 0, sX, 32, 32);  // A operand T: [row i][k = t]; B operand X22: sX[(32 + col) * TLD + 32 + t]
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const double v = -acc2[j][e];
+        sX[(32 + M32_COL(j, e)) * TLD + M32_ROW] = v;
+        sXT[M32_ROW * TLD + 32 + M32_COL(j, e)] = v;
+      }
+  }
+  __syncthreads();
+}
 
 // ---- cluster base case ----------------------------------------------------------------------------------------
 // W (nb x nb, upper read, destroyed) -> R, Ri, RiT blocks (full nb x nb blocks written: zeros in the other triangle).
+// Per block column jb:   [row panel over the cluster]  barrier  [trailing update over 7 CTAs  ||  the 8th: diagonal tile of
+// the next column first, then its leaf (lookahead)]  barrier.
 __global__ void __cluster_dims__(BC_CLUSTER, 1, 1) __launch_bounds__(256, 1)
     basecase_kernel(int nb, double* __restrict__ W, long long ldw, double* __restrict__ R, long long ldr, double* __restrict__ Ri,
                     long long ldri, double* __restrict__ RiT, long long ldrit, int* __restrict__ info, long long* __restrict__ dbg) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   double* sA = sm;                     // tile / leaf array a
   double* sB = sm + TILE_DOUBLES;      // tile / leaf array r
   double* sT = sm + 2 * TILE_DOUBLES;  // tile / leaf scratch
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int T = nb >> 6;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
   double acc[4][2][2];
   int dbgi = 0;
 #define DBG_STAMP() do { if (dbg && rank == 0 && threadIdx.x == 0) dbg[dbgi++] = clock64(); } while (0)
   DBG_STAMP();
 
+  double* sU = sm + 3 * TILE_DOUBLES;  // fourth tile (fast leaf only)
+  auto do_leaf = [&](int jb) {
+    const long long o = (long long)jb * 64;
+    __syncthreads();  // the caller's global writes (trailing update of this very tile) are complete block-wide
+    tile_load(sA, W + o + o * ldw, ldw);
+    __syncthreads();
+    if (dbg && jb == 0 && threadIdx.x == 0) dbg[20] = clock64();
+    leaf64_fast(sA, sB, sT, sU, sm + 4 * TILE_DOUBLES, info, jb * 64, (dbg && jb == 0) ? dbg + 24 : nullptr);
+    if (dbg && jb == 0 && threadIdx.x == 0) dbg[21] = clock64();
+    tile_store<false>(R + o + o * ldr, ldr, sB);
+    tile_store<false>(Ri + o + o * ldri, ldri, sT);
+    tile_store<false>(RiT + o + o * ldrit, ldrit, sU);
+    __syncthreads();
+  };
+  // trailing tile (i, j) of step jb: W(i, j) -= R(jb, i)^T R(jb, j)
+  auto do_trailing = [&](int jb, int i, int j) {
+    const long long o = (long long)jb * 64;
+    __syncthreads();
+    tile_load(sA, R + o + (long long)i * 64 * ldr, ldr);
+    tile_load(sB, R + o + (long long)j * 64 * ldr, ldr);
+    __syncthreads();
+    acc_zero(acc);
+    tile_mma(acc, sA, sB);
+    acc_to_smem_colmajor(acc, sT, -1.0);
+    __syncthreads();
+    tile_store<true>(W + (long long)i * 64 + (long long)j * 64 * ldw, ldw, sT);
+  };
+
+  if (rank == 0) do_leaf(0);
+  DBG_STAMP();
+  __threadfence();
+  cluster.sync();
+  DBG_STAMP();
   // ---------------- Cholesky: right-looking over 64-wide block columns ----------------
   for (int jb = 0; jb < T; jb++) {
     const long long o = (long long)jb * 64;
-    if (rank == (jb % BC_CLUSTER)) {  // diagonal block
-      leaf_load(64, W + o + o * ldw, ldw, sA);
-      __syncthreads();
-      leaf_factor_invert(64, sA, sB, sT, info, jb * 64);
-      leaf_store(64, sA, sB, R + o + o * ldr, ldr, Ri + o + o * ldri, ldri, RiT + o + o * ldrit, ldrit);
-    }
-    if (jb == 0) DBG_STAMP();
-    __threadfence();
-    cluster.sync();
-    if (jb == 0) DBG_STAMP();
     // row panel: R(jb, j) = Rinv_jj^T W(jb, j), j > jb
     int work = 0;
     for (int j = jb + 1; j < T; j++, work++) {
@@ -219,41 +442,32 @@ __global__ void __cluster_dims__(BC_CLUSTER, 1, 1) __launch_bounds__(256, 1)
       tile_load(sB, W + o + (long long)j * 64 * ldw, ldw);            // B[k][c] = W(jb rows, j cols)
       __syncthreads();
       acc_zero(acc);
-      tile_mma(acc, sA, sB, 64);
-      double* out = R + o + (long long)j * 64 * ldr;
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int jj = 0; jj < 2; jj++)
-#pragma unroll
-          for (int e = 0; e < 2; e++) out[TILE_ROW(i) + (long long)TILE_COL(jj, e) * ldr] = acc[i][jj][e];
+      tile_mma(acc, sA, sB);
+      acc_to_smem_colmajor(acc, sT, 1.0);
+      __syncthreads();
+      tile_store<false>(R + o + (long long)j * 64 * ldr, ldr, sT);
     }
     if (jb == 0) DBG_STAMP();
     __threadfence();
     cluster.sync();
     if (jb == 0) DBG_STAMP();
-    // trailing update: W(i, j) -= R(jb, i)^T R(jb, j), jb < i <= j
-    work = 0;
-    for (int j = jb + 1; j < T; j++)
-      for (int i = jb + 1; i <= j; i++, work++) {
-        if (work % BC_CLUSTER != rank) continue;
-        __syncthreads();
-        tile_load(sA, R + o + (long long)i * 64 * ldr, ldr);
-        tile_load(sB, R + o + (long long)j * 64 * ldr, ldr);
-        __syncthreads();
-        acc_zero(acc);
-        tile_mma(acc, sA, sB, 64);
-        double* out = W + (long long)i * 64 + (long long)j * 64 * ldw;
-#pragma unroll
-        for (int ii = 0; ii < 4; ii++)
-#pragma unroll
-          for (int jj = 0; jj < 2; jj++)
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-              double* p = out + TILE_ROW(ii) + (long long)TILE_COL(jj, e) * ldw;
-              *p = __ldcg(p) - acc[ii][jj][e];
-            }
+    if (jb + 1 < T) {
+      const int leaf_rank = (jb + 1) % BC_CLUSTER;
+      if (rank == leaf_rank) {
+        do_trailing(jb, jb + 1, jb + 1);   // lookahead: finish the next diagonal block first ...
+        __threadfence_block();
+        do_leaf(jb + 1);                   // ... and factor it while the other CTAs update the rest
+      } else {
+        const int slot = rank > leaf_rank ? rank - 1 : rank;
+        work = 0;
+        for (int j = jb + 1; j < T; j++)
+          for (int i = jb + 1; i <= j; i++) {
+            if (i == jb + 1 && j == jb + 1) continue;
+            if (work++ % (BC_CLUSTER - 1) != slot) continue;
+            do_trailing(jb, i, j);
+          }
       }
+    }
     if (jb == 0) DBG_STAMP();
     __threadfence();
     cluster.sync();
@@ -280,32 +494,20 @@ __global__ void __cluster_dims__(BC_CLUSTER, 1, 1) __launch_bounds__(256, 1)
         tile_load(sA, RiT + (long long)k * 64 + (long long)i * 64 * ldrit, ldrit);  // A[kk][ii] = RiT(k blk, i blk) = Rinv(i, k)^T
         tile_load(sB, R + (long long)k * 64 + (long long)j * 64 * ldr, ldr);
         __syncthreads();
-        tile_mma(acc, sA, sB, 64);
+        tile_mma(acc, sA, sB);
       }
       __syncthreads();
-      // S (64 x 64, rows i, cols t) -> shared as the next A operand: A[row i][k = t]
-#pragma unroll
-      for (int ii = 0; ii < 4; ii++)
-#pragma unroll
-        for (int jj = 0; jj < 2; jj++)
-#pragma unroll
-          for (int e = 0; e < 2; e++) sT[TILE_ROW(ii) * TLD + TILE_COL(jj, e)] = acc[ii][jj][e];
+      acc_to_smem_rowmajor(acc, sT, 1.0);                                       // S as the next A operand: A[row i][k = t]
       tile_load(sB, Ri + (long long)j * 64 + (long long)j * 64 * ldri, ldri);  // B[t][c] = Rinv_jj(t, c)
       __syncthreads();
       acc_zero(acc);
-      tile_mma(acc, sT, sB, 64);
-      double* o1 = Ri + (long long)i * 64 + (long long)j * 64 * ldri;
-      double* o2 = RiT + (long long)j * 64 + (long long)i * 64 * ldrit;
-#pragma unroll
-      for (int ii = 0; ii < 4; ii++)
-#pragma unroll
-        for (int jj = 0; jj < 2; jj++)
-#pragma unroll
-          for (int e = 0; e < 2; e++) {
-            const double v = -acc[ii][jj][e];
-            o1[TILE_ROW(ii) + (long long)TILE_COL(jj, e) * ldri] = v;
-            o2[TILE_COL(jj, e) + (long long)TILE_ROW(ii) * ldrit] = v;
-          }
+      tile_mma(acc, sT, sB);
+      __syncthreads();
+      acc_to_smem_colmajor(acc, sA, -1.0);  // value(row, col) at sA[col][row]
+      acc_to_smem_rowmajor(acc, sB, -1.0);  // value(row, col) at sB[row][col]
+      __syncthreads();
+      tile_store<false>(Ri + (long long)i * 64 + (long long)j * 64 * ldri, ldri, sA);
+      tile_store_from_rowmajor(RiT + (long long)j * 64 + (long long)i * 64 * ldrit, ldrit, sB);
     }
     __threadfence();
     cluster.sync();
@@ -335,7 +537,7 @@ capital_status_t leaf_cholinv(capital_ctx* ctx, cudaStream_t st, int nb, const d
 capital_status_t basecase_cholinv(capital_ctx* ctx, cudaStream_t st, int nb, double* W, int64_t ldw, double* R, int64_t ldr, double* Ri,
                                   int64_t ldri, double* RiT, int64_t ldrit) {
   if (nb % 64 != 0 || nb < 64 || nb > BASECASE_MAX || RiT == nullptr) return CAPITAL_ERR_INVALID;
-  constexpr int smem = 3 * TILE_DOUBLES * (int)sizeof(double);
+  constexpr int smem = (4 * TILE_DOUBLES + 64) * (int)sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
     CAP_CUDA(cudaFuncSetAttribute(basecase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -348,11 +550,13 @@ capital_status_t basecase_cholinv(capital_ctx* ctx, cudaStream_t st, int nb, dou
   }
   basecase_kernel<<<BC_CLUSTER, 256, smem, st>>>(nb, W, ldw, R, ldr, Ri, ldri, RiT, ldrit, ctx->d_info, dbg);
   if (dbg) {
-    long long h[16];
+    long long h[32];
     CAP_CUDA(cudaMemcpyAsync(h, dbg, sizeof(h), cudaMemcpyDeviceToHost, st));
     CAP_CUDA(cudaStreamSynchronize(st));
-    fprintf(stderr, "[bc nb=%d] leaf0=%lld bar=%lld panel0=%lld bar=%lld trail0=%lld bar=%lld | chol_total=%lld inverse=%lld total=%lld cycles\n", nb,
+    fprintf(stderr, "[bc nb=%d] leaf0=%lld bar=%lld panel0=%lld bar=%lld trail0+leaf1=%lld bar=%lld | chol_total=%lld inverse=%lld total=%lld cycles\n", nb,
             h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5], h[7] - h[0], h[8] - h[7], h[8] - h[0]);
+    fprintf(stderr, "   leaf64: load=%lld total=%lld | warp32: pre=%lld potrf=%lld trtri=%lld store=%lld\n", h[20] - h[0], h[21] - h[20], h[24] - h[20],
+            h[25] - h[24], h[26] - h[25], h[27] - h[26]);
   }
   ctx->counters.kernel_launches++;
   ctx->counters.leaf_launches++;

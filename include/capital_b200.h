@@ -93,6 +93,8 @@ capital_status_t capital_last_factor_ms(const capital_ctx* ctx, float* ms);
  * begin arms it; end synchronizes and returns the summed launch durations, the algorithmic flops of those
  * launches (structure exploited) and their count.  Used by bench.py for the roofline line. */
 capital_status_t capital_profile_begin(capital_ctx* ctx);
+/* enabled = 0 runs the recursion on a single stream (no deferred-update overlap): isolates per-kernel durations. */
+capital_status_t capital_set_overlap(capital_ctx* ctx, int enabled);
 capital_status_t capital_profile_end(capital_ctx* ctx, double* kernel_ms, double* kernel_flops, int64_t* launches);
 
 /* ---- generators (device kernels; bit-exact with the reference's drand48-based ones) ---------- */

@@ -58,6 +58,24 @@ def main():
             res = cb.cholinv.residual(A, args, topo)
             ok &= er < 2e-13 and ei < 2e-13 and zd and res < 1e-12
             msgs.append(f"oracle n={n} ci={ci}: dR={er:.1e} dRinv={ei:.1e} zero-diag-slots={zd} res={res:.1e}")
+    if world in (2, 4):
+        # not reference grids (summa.hpp needs c == d): the library's own 2x1x1 / 1x2x2 schedules, checked against the oracle
+        c = 2 if world == 2 else 1
+        topo = cb.topo.square(world, rank, c)
+        d = topo.d
+        for n, ci, bcm in ((512, 1, -2), (2048, 0, -3), (3072, 1, -3)):
+            A = cb.matrix(n, n, d, d).distribute_symmetric(topo)
+            args = cb.cholinv.info(ci, 1, bcm, "U")
+            cb.cholinv.factor(A, args, topo)
+            L = n // d
+            r_o, ri_o = co.cholinv(co.spd_global(n), bool(ci), 1, co.bc_dimension(L, c, d, bcm), d=d)
+            R = cb.cholinv.construct_R(args).cpu().numpy()
+            Ri = cb.cholinv.construct_Rinv(args).cpu().numpy()
+            er = np.abs(R - np.triu(co.cyclic_local(r_o, d, d, topo.x, topo.y))).max() / np.abs(r_o).max()
+            ei = np.abs(Ri - np.triu(co.cyclic_local(ri_o, d, d, topo.x, topo.y))).max() / np.abs(ri_o).max()
+            res = cb.cholinv.residual(A, args, topo)
+            ok &= er < 2e-13 and ei < 2e-13 and res < 1e-12
+            msgs.append(f"grid {c}x{d}x{d} n={n} ci={ci}: dR={er:.1e} dRinv={ei:.1e} res={res:.1e}")
     # --- 1D CholeskyQR2 on all ranks ---
     qt = cb.topo.rect(world, rank, 1)
     if world == 8:

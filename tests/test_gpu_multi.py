@@ -24,3 +24,9 @@ def test_cacqr_1d_on_2_gpus():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     _run(2)
+
+
+def test_cholinv_1x2x2_on_4_gpus():
+    if torch.cuda.device_count() < 4:
+        pytest.skip("needs 4 GPUs")
+    _run(4)
