@@ -69,7 +69,8 @@ struct HostIO {
   bool packed = true;
   std::vector<std::pair<int64_t, cudaEvent_t>> chunks;  // (col_end, arrived)
   int64_t waited = 0;
-  int64_t cols_out = 0;
+  int64_t cols_out = 0, rinv_cols_out = 0;
+  bool rinv_streams = false;  // Rinv columns right of the top split are final as soon as R's are (complete_inv == 0)
   cudaEvent_t e_out = nullptr;
 };
 capital_status_t io_event(capital_ctx* ctx, cudaEvent_t* e) {
@@ -93,22 +94,30 @@ capital_status_t hostio_need_cols(void* user, cudaStream_t st, int64_t col_end) 
     }
   return CAPITAL_OK;
 }
-// columns [0, s1) of R and Rinv are final: pack them (a contiguous prefix of the packed triangle) and start their D2H
-capital_status_t hostio_left_done(void* user, cudaStream_t st, int64_t s1) {
+// columns [cols_out, col_end) of R are final (and of Rinv too when the top-level inverse block is skipped, complete_inv == 0:
+// then Rinv's columns right of the top split only hold the right child's own inverse): pack them -- a contiguous range of
+// the packed triangle -- and start their D2H while the rest of the factorization runs.
+capital_status_t hostio_left_done(void* user, cudaStream_t st, int64_t col_end, int depth) {
   HostIO* io = (HostIO*)user;
   capital_ctx* ctx = io->ctx;
-  const size_t cnt = (size_t)s1 * (s1 + 1) / 2;
-  CAP_TRY(pack_upper(ctx, st, io->L, io->Rm, io->ld, io->dR, 0, 0, s1));
-  CAP_TRY(pack_upper(ctx, st, io->L, io->Ri, io->ld, io->dRinv, 0, 0, s1));
+  const int64_t c0 = io->cols_out;
+  if (col_end <= c0) return CAPITAL_OK;
+  // Rinv: left of the top split always; the next range only when the top-level inverse block is skipped (deeper ranges still
+  // miss the off-diagonal inverse blocks of the right-spine ancestors, computed after their right children)
+  const bool rinv_too = depth == 0 || (depth == 1 && io->rinv_streams && io->rinv_cols_out == c0);
+  const size_t off = (size_t)c0 * (c0 + 1) / 2, cnt = (size_t)col_end * (col_end + 1) / 2 - off;
+  CAP_TRY(pack_upper(ctx, st, io->L, io->Rm, io->ld, io->dR, 0, c0, col_end));
+  if (rinv_too) CAP_TRY(pack_upper(ctx, st, io->L, io->Ri, io->ld, io->dRinv, 0, c0, col_end));
   cudaEvent_t e;
   CAP_TRY(io_event(ctx, &e));
   CAP_CUDA(cudaEventRecord(e, st));
   CAP_CUDA(cudaStreamWaitEvent(ctx->copy_out, e, 0));
-  if (io->hR) { CAP_CUDA(cudaMemcpyAsync(io->hR, io->dR, cnt * 8, cudaMemcpyDeviceToHost, ctx->copy_out)); ctx->counters.d2h_bytes += (int64_t)cnt * 8; }
-  if (io->hRinv) { CAP_CUDA(cudaMemcpyAsync(io->hRinv, io->dRinv, cnt * 8, cudaMemcpyDeviceToHost, ctx->copy_out)); ctx->counters.d2h_bytes += (int64_t)cnt * 8; }
+  if (io->hR) { CAP_CUDA(cudaMemcpyAsync(io->hR + off, io->dR + off, cnt * 8, cudaMemcpyDeviceToHost, ctx->copy_out)); ctx->counters.d2h_bytes += (int64_t)cnt * 8; }
+  if (io->hRinv && rinv_too) { CAP_CUDA(cudaMemcpyAsync(io->hRinv + off, io->dRinv + off, cnt * 8, cudaMemcpyDeviceToHost, ctx->copy_out)); ctx->counters.d2h_bytes += (int64_t)cnt * 8; }
   CAP_TRY(io_event(ctx, &io->e_out));
   CAP_CUDA(cudaEventRecord(io->e_out, ctx->copy_out));
-  io->cols_out = s1;
+  io->cols_out = col_end;
+  if (rinv_too) io->rinv_cols_out = col_end;
   return CAPITAL_OK;
 }
 }  // namespace
@@ -322,6 +331,7 @@ capital_status_t capital_cholinv_factor_f64(capital_ctx* ctx, const double* A_lo
   io.ctx = ctx; io.L = L; io.ld = ld; io.Rm = Rm; io.Ri = Ri; io.dR = dR; io.dRinv = dRinv;
   io.hR = (dR != R_local) ? R_local : nullptr; io.hRinv = (dRinv != Rinv_local) ? Rinv_local : nullptr;
   io.packed = ostruct == CAPITAL_UPPERTRI_PACKED;
+  io.rinv_streams = args->complete_inv == 0;
   CholinvHooks hooks{&io, nullptr, nullptr};
   if (!cap_is_device_ptr(A_local)) {
     cudaEvent_t e0;
@@ -331,14 +341,16 @@ capital_status_t capital_cholinv_factor_f64(capital_ctx* ctx, const double* A_lo
     const int64_t chunk = round_up(ceil_div(L, 16), 64);
     for (int64_t c0 = 0; c0 < L; c0 += chunk) {
       const int64_t nc = (c0 + chunk <= L) ? chunk : L - c0;
-      CAP_CUDA(cudaMemcpy2DAsync(W + c0 * ld, (size_t)ld * 8, A_local + c0 * L, (size_t)L * 8, (size_t)L * 8, (size_t)nc,
+      // only the upper triangle of A is read (serialize<uppertri>(A -> R), cholinv.hpp:13): rows [0, c0 + nc) of this chunk
+      const int64_t rows = c0 + nc;
+      CAP_CUDA(cudaMemcpy2DAsync(W + c0 * ld, (size_t)ld * 8, A_local + c0 * L, (size_t)L * 8, (size_t)rows * 8, (size_t)nc,
                                  cudaMemcpyHostToDevice, ctx->copy_in));
+      ctx->counters.h2d_bytes += rows * nc * 8;
       cudaEvent_t e;
       CAP_TRY(io_event(ctx, &e));
       CAP_CUDA(cudaEventRecord(e, ctx->copy_in));
       io.chunks.push_back({c0 + nc, e});
     }
-    ctx->counters.h2d_bytes += (int64_t)L * L * 8;
     hooks.need_cols = hostio_need_cols;
   } else {
     CAP_TRY(copy_block(ctx, st, L, L, A_local, L, W, ld));  // serialize(A -> R), cholinv.hpp:13
@@ -347,12 +359,18 @@ capital_status_t capital_cholinv_factor_f64(capital_ctx* ctx, const double* A_lo
   const int64_t bc = capital_cholinv_bc_dimension(L, g.c, g.d, args->bc_mult_dim);
   CAP_TRY(cholinv_local(ctx, st, L, W, ld, Rm, ld, Ri, ld, RiT, ld, args->complete_inv != 0, bc, (int)args->split, &hooks));
   if (ostruct == CAPITAL_UPPERTRI_PACKED) {
-    const int64_t c0 = io.cols_out;  // columns [0, c0) already packed (and on their way to the host)
-    const size_t off = (size_t)c0 * (c0 + 1) / 2, cnt = out_count - off;
-    CAP_TRY(pack_upper(ctx, st, L, Rm, ld, dR, 0, c0, L));
-    if (io.hR) { CAP_CUDA(cudaMemcpyAsync(io.hR + off, dR + off, cnt * 8, cudaMemcpyDeviceToHost, st)); ctx->counters.d2h_bytes += (int64_t)cnt * 8; }
-    CAP_TRY(pack_upper(ctx, st, L, Ri, ld, dRinv, 0, c0, L));
-    if (io.hRinv) { CAP_CUDA(cudaMemcpyAsync(io.hRinv + off, dRinv + off, cnt * 8, cudaMemcpyDeviceToHost, st)); ctx->counters.d2h_bytes += (int64_t)cnt * 8; }
+    {  // columns [0, c0) are already packed (and on their way to the host)
+      const int64_t c0 = io.cols_out;
+      const size_t off = (size_t)c0 * (c0 + 1) / 2, cnt = out_count - off;
+      CAP_TRY(pack_upper(ctx, st, L, Rm, ld, dR, 0, c0, L));
+      if (io.hR) { CAP_CUDA(cudaMemcpyAsync(io.hR + off, dR + off, cnt * 8, cudaMemcpyDeviceToHost, st)); ctx->counters.d2h_bytes += (int64_t)cnt * 8; }
+    }
+    {
+      const int64_t c0 = io.rinv_cols_out;
+      const size_t off = (size_t)c0 * (c0 + 1) / 2, cnt = out_count - off;
+      CAP_TRY(pack_upper(ctx, st, L, Ri, ld, dRinv, 0, c0, L));
+      if (io.hRinv) { CAP_CUDA(cudaMemcpyAsync(io.hRinv + off, dRinv + off, cnt * 8, cudaMemcpyDeviceToHost, st)); ctx->counters.d2h_bytes += (int64_t)cnt * 8; }
+    }
     if (io.e_out) CAP_CUDA(cudaStreamWaitEvent(st, io.e_out, 0));  // the early D2H of the left half
   } else {
     CAP_TRY(triu_copy(ctx, st, L, Rm, ld, dR, L, 0));

@@ -36,6 +36,7 @@ struct Rec {
   int split;
   const CholinvHooks* hooks;
   int64_t far_min;  // trailing updates smaller than this are not split
+  int64_t total;      // size of the top-level block
   bool base_aligned;  // all four buffers 16-byte aligned with even leading dimensions (cluster kernel uses 16-byte accesses)
 };
 
@@ -86,7 +87,8 @@ capital_status_t rec(Rec& r, int64_t o, int64_t n, bool complete, cudaEvent_t pe
   double* RiT21 = RiT + s1;
 
   CAP_TRY(rec(r, o, s1, true, nullptr, depth + 1));
-  if (depth == 0 && r.hooks && r.hooks->left_done) CAP_TRY(r.hooks->left_done(r.hooks->user, r.M, s1));
+  // right spine only (o + n == total size): everything left of column o + s1 is final for R
+  if (depth <= 3 && o + n == r.total && r.hooks && r.hooks->left_done) CAP_TRY(r.hooks->left_done(r.hooks->user, r.M, o + s1, depth));
   if (r.hooks && r.hooks->need_cols) CAP_TRY(r.hooks->need_cols(r.hooks->user, r.M, o + n));
   if (pending) CAP_CUDA(cudaStreamWaitEvent(r.M, pending, 0));  // the parent's deferred update covers W12 and W22
   // "trsm" via the inverse (cholinv.hpp:116-122): R12 = Rinv11^T A12
@@ -148,7 +150,7 @@ capital_status_t cholinv_local(capital_ctx* ctx, cudaStream_t st, int64_t n, dou
     if (S) CAP_CUDA(cudaStreamWaitEvent(S, e_in, 0));
   }
   const bool aligned = ((((uintptr_t)W | (uintptr_t)R | (uintptr_t)Ri | (uintptr_t)RiT) & 15) == 0) && !((ldw | ldr | ldri | ldrit) & 1);
-  Rec r{ctx, M, S, W, R, Ri, RiT, ldw, ldr, ldri, ldrit, bc, split, hooks, 2048, aligned};
+  Rec r{ctx, M, S, W, R, Ri, RiT, ldw, ldr, ldri, ldrit, bc, split, hooks, 2048, n, aligned};
   CAP_TRY(rec(r, 0, n, complete_top, nullptr, 0));
   if (M != st) {
     if (S) {  // join the deferred stream (all its work has been consumed through events, this is just the fence)

@@ -128,12 +128,13 @@ capital_status_t leaf_cholinv(capital_ctx* ctx, cudaStream_t st, int nb, const d
 // ---- cholinv.cu -------------------------------------------------------------------------------
 // local (single-GPU) recursive CholInv on dense n x n blocks; W is destroyed (Schur complements).
 // Optional callbacks of the top-level call (host-pointer path): `need_cols` makes `st` wait until columns [0, col_end)
-// of W have arrived from the host; `left_done` fires once, after the top-level left child, when columns [0, s1) of R
+// of W have arrived from the host; `left_done` fires after each left child on the right spine (depth <= 3), when columns
+// [0, col_end) of R are final
 // and Rinv are final.
 struct CholinvHooks {
   void* user;
   capital_status_t (*need_cols)(void* user, cudaStream_t st, int64_t col_end);
-  capital_status_t (*left_done)(void* user, cudaStream_t st, int64_t s1);
+  capital_status_t (*left_done)(void* user, cudaStream_t st, int64_t col_end, int depth);
 };
 capital_status_t cholinv_local(capital_ctx* ctx, cudaStream_t st, int64_t n, double* W, int64_t ldw, double* R, int64_t ldr,
                                double* Ri, int64_t ldri, double* RiT, int64_t ldrit, bool complete_top, int64_t bc, int split,

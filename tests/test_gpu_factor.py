@@ -66,7 +66,8 @@ def test_cholinv_host_pointers_and_reuse(topo):
         ctx.reset_counters()
         cb.cholinv.factor(A, args, topo)
         cnt = ctx.counters()
-        assert cnt.h2d_bytes == n * n * 8 and cnt.d2h_bytes == 2 * (n * (n + 1) // 2) * 8 and cnt.kernel_launches > 0
+        # only the upper triangle of A travels (column chunks, rows 0..chunk end)
+        assert n * (n + 1) // 2 * 8 <= cnt.h2d_bytes <= n * n * 8 * 0.6 and cnt.d2h_bytes == 2 * (n * (n + 1) // 2) * 8 and cnt.kernel_launches > 0
     assert not args.R.is_cuda
     r_o, ri_o = co.cholinv(co.spd_global(n), True, 1, co.bc_dimension(n, 1, 1, -2))
     assert np.abs(co.unpack_upper(args.R.numpy(), n) - r_o).max() < 1e-12
