@@ -484,30 +484,59 @@ __global__ void __cluster_dims__(BC_CLUSTER, 1, 1) __launch_bounds__(256, 1)
           R[(long long)i * 64 + (idx & 63) + ((long long)j * 64 + (idx >> 6)) * ldr] = 0.0;
       }
   }
-  // ---------------- inverse: block column j from the columns before it ----------------
-  //   Rinv(i, j) = -[ sum_{k=i}^{j-1} Rinv(i, k) R(k, j) ] Rinv(j, j),  i < j
-  for (int j = 1; j < T; j++) {
-    for (int i = rank; i < j; i += BC_CLUSTER) {
-      acc_zero(acc);
-      for (int k = i; k < j; k++) {
-        __syncthreads();
-        tile_load(sA, RiT + (long long)k * 64 + (long long)i * 64 * ldrit, ldrit);  // A[kk][ii] = RiT(k blk, i blk) = Rinv(i, k)^T
-        tile_load(sB, R + (long long)k * 64 + (long long)j * 64 * ldr, ldr);
-        __syncthreads();
-        tile_mma(acc, sA, sB);
-      }
-      __syncthreads();
-      acc_to_smem_rowmajor(acc, sT, 1.0);                                       // S as the next A operand: A[row i][k = t]
-      tile_load(sB, Ri + (long long)j * 64 + (long long)j * 64 * ldri, ldri);  // B[t][c] = Rinv_jj(t, c)
-      __syncthreads();
-      acc_zero(acc);
-      tile_mma(acc, sT, sB);
-      __syncthreads();
-      acc_to_smem_colmajor(acc, sA, -1.0);  // value(row, col) at sA[col][row]
-      acc_to_smem_rowmajor(acc, sB, -1.0);  // value(row, col) at sB[row][col]
-      __syncthreads();
-      tile_store<false>(Ri + (long long)i * 64 + (long long)j * 64 * ldri, ldri, sA);
-      tile_store_from_rowmajor(RiT + (long long)j * 64 + (long long)i * 64 * ldrit, ldrit, sB);
+  // ---------------- inverse by recursive doubling over 64-wide blocks ----------------
+  //   level bs (1, 2, 4 tiles): for every pair of neighbouring diagonal blocks [o, o+bs) / [o+bs, o+2bs):
+  //     phase 1   T(i, j)    =  sum_{k = i}^{o+bs-1} Rinv(i, k) R(k, j)          (stored transposed in the dead W block)
+  //     phase 2   Rinv(i, j) = -sum_{k = o+bs}^{j}   T(i, k)    Rinv(k, j)
+  //   Depth 18 tile products for T = 8 instead of 35 for the column-by-column order; W is dead after the Cholesky phase.
+  for (int bs = 1; bs < T; bs <<= 1) {
+    const int span = 2 * bs;
+    // phase 1
+    int work = 0;
+    for (int o = 0; o + bs < T; o += span) {
+      const int jend = min(o + span, T);
+      for (int j = o + bs; j < jend; j++)
+        for (int i = o; i < o + bs; i++, work++) {
+          if (work % BC_CLUSTER != rank) continue;
+          acc_zero(acc);
+          for (int k = i; k < o + bs; k++) {
+            __syncthreads();
+            tile_load(sA, RiT + (long long)k * 64 + (long long)i * 64 * ldrit, ldrit);  // A[row i_][k_] = Rinv(i, k)
+            tile_load(sB, R + (long long)k * 64 + (long long)j * 64 * ldr, ldr);
+            __syncthreads();
+            tile_mma(acc, sA, sB);
+          }
+          __syncthreads();
+          acc_to_smem_rowmajor(acc, sT, 1.0);  // value(i_, t_) at sT[i_ * TLD + t_]
+          __syncthreads();
+          // T(i, j)^T into the W tile (j, i): W[(j*64 + t_) + (i*64 + i_) * ldw] = T(i, j)(i_, t_)
+          tile_store_from_rowmajor(W + (long long)j * 64 + (long long)i * 64 * ldw, ldw, sT);
+        }
+    }
+    __threadfence();
+    cluster.sync();
+    // phase 2
+    work = 0;
+    for (int o = 0; o + bs < T; o += span) {
+      const int jend = min(o + span, T);
+      for (int j = o + bs; j < jend; j++)
+        for (int i = o; i < o + bs; i++, work++) {
+          if (work % BC_CLUSTER != rank) continue;
+          acc_zero(acc);
+          for (int k = o + bs; k <= j; k++) {
+            __syncthreads();
+            tile_load(sA, W + (long long)k * 64 + (long long)i * 64 * ldw, ldw);        // A[row i_][t_] = T(i, k)(i_, t_)
+            tile_load(sB, Ri + (long long)k * 64 + (long long)j * 64 * ldri, ldri);     // B[t_][c] = Rinv(k, j)
+            __syncthreads();
+            tile_mma(acc, sA, sB);
+          }
+          __syncthreads();
+          acc_to_smem_colmajor(acc, sA, -1.0);  // value(row, col) at sA[col][row]
+          acc_to_smem_rowmajor(acc, sB, -1.0);  // value(row, col) at sB[row][col]
+          __syncthreads();
+          tile_store<false>(Ri + (long long)i * 64 + (long long)j * 64 * ldri, ldri, sA);
+          tile_store_from_rowmajor(RiT + (long long)j * 64 + (long long)i * 64 * ldrit, ldrit, sB);
+        }
     }
     __threadfence();
     cluster.sync();
