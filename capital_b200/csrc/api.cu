@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "dist.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 capital_status_t capital_ctx::workspace(const std::string& name, size_t bytes, void** out) {
   capital_ctx* ctx = this;
@@ -191,6 +192,7 @@ capital_status_t capital_create(capital_ctx** out, const capital_grid_t* grid, i
   ok = ok && cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn != nullptr;
   if (!ok) { capital_destroy(ctx); return CAPITAL_ERR_CUDA; }
   ctx->encode = (cuTensorMapEncodeTiled_fn)fn;
+  if (const char* e = getenv("CAPITAL_KCHUNK")) ctx->kchunk = atoll(e);
   *out = ctx;
   return CAPITAL_OK;
 }

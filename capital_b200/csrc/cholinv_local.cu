@@ -37,6 +37,7 @@ struct Rec {
   const CholinvHooks* hooks;
   int64_t far_min;  // trailing updates smaller than this are not split
   int64_t total;      // size of the top-level block
+  int64_t kchunk;     // k extent of one launch of deferred work (bounds how long a deferred tile holds an SM)
   bool base_aligned;  // all four buffers 16-byte aligned with even leading dimensions (cluster kernel uses 16-byte accesses)
 };
 
@@ -106,9 +107,9 @@ capital_status_t rec(Rec& r, int64_t o, int64_t n, bool complete, cudaEvent_t pe
   const int64_t h = choose_split(r, o + s1, s2, true);
   if (use_side && h > 0 && s2 >= r.far_min) {
     CAP_TRY(gemm_tn(ctx, r.M, h, h, s1, -1.0, R12, ldr, R12, ldr, 1.0, W22, ldw, CAPITAL_GEMM_C_UPPER));
-    CAP_TRY(gemm_tn(ctx, r.S, h, s2 - h, s1, -1.0, R12, ldr, R12 + h * ldr, ldr, 1.0, W22 + h * ldw, ldw, 0));
-    CAP_TRY(gemm_tn(ctx, r.S, s2 - h, s2 - h, s1, -1.0, R12 + h * ldr, ldr, R12 + h * ldr, ldr, 1.0, W22 + h * ldw + h, ldw,
-                    CAPITAL_GEMM_C_UPPER));
+    CAP_TRY(gemm_tn_chunked(ctx, r.S, h, s2 - h, s1, -1.0, R12, ldr, R12 + h * ldr, ldr, 1.0, W22 + h * ldw, ldw, 0, r.kchunk));
+    CAP_TRY(gemm_tn_chunked(ctx, r.S, s2 - h, s2 - h, s1, -1.0, R12 + h * ldr, ldr, R12 + h * ldr, ldr, 1.0, W22 + h * ldw + h, ldw,
+                            CAPITAL_GEMM_C_UPPER, r.kchunk));
     CAP_TRY(new_event(ctx, &e_far));
     CAP_CUDA(cudaEventRecord(e_far, r.S));
   } else {
@@ -117,7 +118,7 @@ capital_status_t rec(Rec& r, int64_t o, int64_t n, bool complete, cudaEvent_t pe
   if (complete) {
     // inverse combine, first half (cholinv.hpp:151): T^T = R12^T Rinv11^T  (B = RiT11, lower triangular) -- nobody needs
     // it before the right child is done, so it goes to the deferred stream.
-    CAP_TRY(gemm_tn(ctx, tS, s2, s1, s1, 1.0, R12, ldr, RiT, ldrit, 0.0, W21, ldw, CAPITAL_GEMM_B_LOWER));
+    CAP_TRY(gemm_tn_chunked(ctx, tS, s2, s1, s1, 1.0, R12, ldr, RiT, ldrit, 0.0, W21, ldw, CAPITAL_GEMM_B_LOWER, use_side ? r.kchunk : 0));
     if (use_side) {
       CAP_TRY(new_event(ctx, &e_tt));
       CAP_CUDA(cudaEventRecord(e_tt, r.S));
@@ -150,7 +151,7 @@ capital_status_t cholinv_local(capital_ctx* ctx, cudaStream_t st, int64_t n, dou
     if (S) CAP_CUDA(cudaStreamWaitEvent(S, e_in, 0));
   }
   const bool aligned = ((((uintptr_t)W | (uintptr_t)R | (uintptr_t)Ri | (uintptr_t)RiT) & 15) == 0) && !((ldw | ldr | ldri | ldrit) & 1);
-  Rec r{ctx, M, S, W, R, Ri, RiT, ldw, ldr, ldri, ldrit, bc, split, hooks, 2048, n, aligned};
+  Rec r{ctx, M, S, W, R, Ri, RiT, ldw, ldr, ldri, ldrit, bc, split, hooks, 2048, n, ctx->kchunk, aligned};
   CAP_TRY(rec(r, 0, n, complete_top, nullptr, 0));
   if (M != st) {
     if (S) {  // join the deferred stream (all its work has been consumed through events, this is just the fence)

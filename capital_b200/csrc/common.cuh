@@ -70,6 +70,7 @@ struct capital_ctx {
   // per-launch timing of the dominant kernel (gemm_tn 128x128), off by default
   struct ProfRec { cudaEvent_t e0, e1; double flops; };
   bool profiling = false;
+  int64_t kchunk = 0;       // k-chunking of deferred GEMMs (env CAPITAL_KCHUNK); measured r01: 0 (off) is fastest, see profiles/r01c_notes.md
   bool no_overlap = false;  // debug / measurement: run the recursion on one stream
   std::vector<cudaEvent_t> prof_pool;
   size_t prof_used = 0;
@@ -93,6 +94,10 @@ struct capital_ctx {
 capital_status_t gemm_tn(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
                          int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags);
 
+capital_status_t gemm_tn_off(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
+                             int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags, int koff);
+capital_status_t gemm_tn_chunked(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
+                                 int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags, int64_t kc);
 capital_status_t gemm_tn_splitk(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
                                 int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int flags);
 

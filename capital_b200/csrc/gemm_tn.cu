@@ -23,6 +23,7 @@ struct GemmParams {
   int M, N, K;
   int rowoffA, rowoffB;  // element offset of the operand's first row inside its (16B-aligned) tensor map
   int flags;
+  int koff;    // row index of this window inside the full operand (k-chunked launches keep the triangular k ranges right)
   int ksplit;  // gridDim.z chunks of the k range; > 1 => epilogue accumulates with atomics (C pre-initialised, beta ignored)
   double alpha, beta;
   double* C;
@@ -84,12 +85,13 @@ __global__ void __launch_bounds__(((BM / WM) * (BN / WN) + 4) * 32, MINB)
   if ((flags & CAPITAL_GEMM_C_UPPER) && m0 > n0 + BN - 1) return;  // tile strictly below the diagonal
 
   int kb = 0, ke = p.K;
-  if (flags & CAPITAL_GEMM_A_UPPER) ke = min(ke, m0 + BM);
-  if (flags & CAPITAL_GEMM_A_LOWER) kb = max(kb, m0);
-  if (flags & CAPITAL_GEMM_B_UPPER) ke = min(ke, n0 + BN);
-  if (flags & CAPITAL_GEMM_B_LOWER) kb = max(kb, n0);
+  if (flags & CAPITAL_GEMM_A_UPPER) ke = min(ke, m0 + BM - p.koff);
+  if (flags & CAPITAL_GEMM_A_LOWER) kb = max(kb, m0 - p.koff);
+  if (flags & CAPITAL_GEMM_B_UPPER) ke = min(ke, n0 + BN - p.koff);
+  if (flags & CAPITAL_GEMM_B_LOWER) kb = max(kb, n0 - p.koff);
   kb &= ~(BK - 1);
   int nk = ke > kb ? (ke - kb + BK - 1) / BK : 0;
+  if (nk == 0 && p.beta == 1.0 && p.ksplit <= 1) return;  // nothing to add (k-chunk entirely outside the operand's triangle)
   if (p.ksplit > 1) {  // this CTA's contiguous chunk of k tiles
     const int per = (nk + p.ksplit - 1) / p.ksplit;
     const int t0 = min(nk, (int)blockIdx.z * per), t1 = min(nk, t0 + per);
@@ -223,14 +225,14 @@ capital_status_t make_map(capital_ctx* ctx, CUtensorMap* map, const double* base
 
 template <class Cfg, int BM, int BN>
 capital_status_t launch(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
-                        int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags, int ksplit) {
+                        int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags, int ksplit, int koff = 0) {
   static bool attr_set = false;
   if (!attr_set) {
     CAP_CUDA(cudaFuncSetAttribute(Cfg::kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem));
     attr_set = true;
   }
   GemmParams p;
-  p.M = (int)m; p.N = (int)n; p.K = (int)k; p.flags = flags; p.alpha = alpha; p.beta = beta; p.C = C; p.ldc = ldc; p.ksplit = ksplit;
+  p.M = (int)m; p.N = (int)n; p.K = (int)k; p.flags = flags; p.alpha = alpha; p.beta = beta; p.C = C; p.ldc = ldc; p.ksplit = ksplit; p.koff = koff;
   // TMA fetches 16-byte granules: a window that starts on an odd row (8-byte aligned only) cannot be addressed by
   // box coordinates, so it is first copied to an aligned scratch (O(k m) bytes against O(k m n) flops; only odd
   // split points of non-power-of-two sizes ever take this path).
@@ -281,8 +283,27 @@ capital_status_t gemm_tn_splitk(capital_ctx* ctx, cudaStream_t st, int64_t m, in
   return launch<CfgSmall, 64, 64>(ctx, st, m, n, k, alpha, A, lda, B, ldb, 1.0, C, ldc, flags, (int)ks);
 }
 
+// Same product issued as a sequence of k-chunked launches (C accumulates).  Used for deferred work on the low-priority
+// stream: a 128x128 tile with k = 8192 occupies its SM for ~1 ms, which would make the latency-critical kernels of the
+// high-priority stream wait that long for an SM; chunks of `kc` bound the wait to kc/16 k-tiles.
+capital_status_t gemm_tn_chunked(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
+                                 int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags, int64_t kc) {
+  if (kc <= 0 || k <= kc + kc / 2) return gemm_tn(ctx, st, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags);
+  for (int64_t k0 = 0; k0 < k; k0 += kc) {
+    const int64_t kk = (k - k0 < kc + kc / 2) ? k - k0 : kc;
+    CAP_TRY(gemm_tn_off(ctx, st, m, n, kk, alpha, A + k0, lda, B + k0, ldb, k0 == 0 ? beta : 1.0, C, ldc, flags, (int)k0));
+    if (kk != kc) break;
+  }
+  return CAPITAL_OK;
+}
+
 capital_status_t gemm_tn(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
                          int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags) {
+  return gemm_tn_off(ctx, st, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags, 0);
+}
+
+capital_status_t gemm_tn_off(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
+                             int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags, int koff) {
   if (m <= 0 || n <= 0) return CAPITAL_OK;
   if (k < 0 || lda < k || ldb < k || ldc < m || (lda & 1) || (ldb & 1) || ((uintptr_t)A & 7) || ((uintptr_t)B & 7)) {
     ctx->set_error("gemm_tn: invalid/unsupported leading dimensions (lda, ldb must be even and >= k)");
@@ -308,12 +329,12 @@ capital_status_t gemm_tn(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n
       CAP_TRY(ctx->prof_event(&e0)); CAP_TRY(ctx->prof_event(&e1));
       CAP_CUDA(cudaEventRecord(e0, st));
     }
-    CAP_TRY((launch<CfgBig, 128, 128>(ctx, st, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags, 1)));
+    CAP_TRY((launch<CfgBig, 128, 128>(ctx, st, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags, 1, koff)));
     if (ctx->profiling) {
       CAP_CUDA(cudaEventRecord(e1, st));
       ctx->prof_recs.push_back({e0, e1, f});
     }
     return CAPITAL_OK;
   }
-  return launch<CfgSmall, 64, 64>(ctx, st, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags, 1);
+  return launch<CfgSmall, 64, 64>(ctx, st, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags, 1, koff);
 }
