@@ -66,6 +66,10 @@ struct capital_ctx {
   void* comm_col = nullptr;
   void* comm_depth = nullptr;
   void* comm_slice = nullptr;
+  cudaStream_t comm_stream = nullptr;  // NCCL stream of the pipelined distributed products
+  std::vector<cudaEvent_t> comm_pool;
+  size_t comm_used = 0;
+  bool dist_pipeline = false;
 
   // per-launch timing of the dominant kernel (gemm_tn 128x128), off by default
   struct ProfRec { cudaEvent_t e0, e1; double flops; };
@@ -95,7 +99,7 @@ capital_status_t gemm_tn(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n
                          int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags);
 
 capital_status_t gemm_tn_off(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
-                             int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags, int koff);
+                             int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags, int koff, int noff = 0);
 capital_status_t gemm_tn_chunked(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
                                  int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags, int64_t kc);
 capital_status_t gemm_tn_splitk(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const double* A,

@@ -15,6 +15,7 @@
 #include "dist.cuh"
 #include <dlfcn.h>
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -89,6 +90,16 @@ __global__ void axpby_kernel(long long rows, long long cols, const double* __res
     C[c * ldc + r] = beta == 0.0 ? v : beta * C[c * ldc + r] + v;
   }
 }
+__global__ void axpby_off_kernel(long long rows, long long cols, const double* __restrict__ P, long long ldp, double beta, double* __restrict__ C,
+                                 long long ldc, int upper_only, long long col0) {
+  const long long total = rows * cols;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long c = idx / rows, r = idx - c * rows;
+    if (upper_only && r > c + col0) continue;
+    const double v = P[c * ldp + r];
+    C[c * ldc + r] = beta == 0.0 ? v : beta * C[c * ldc + r] + v;
+  }
+}
 // gathered[(x' + d y')] = local block (s x s, ld lds) of slice rank x' + d y'  ->  dense (s d) x (s d) block, upper part
 // (util::block_to_cyclic_*, util.hpp:56-133)
 __global__ void blocks_to_dense_kernel(int s, int d, const double* __restrict__ gathered, long long lds, double* __restrict__ dense,
@@ -138,6 +149,9 @@ struct Dist {
 // pack a (rows x cols) window into a contiguous buffer with even leading dimension
 inline int64_t packed_ld(int64_t rows) { return round_up(rows, 2); }
 
+capital_status_t product_pipelined(Dist& D, int64_t m, int64_t n, int64_t k, double alpha, const double* X, int64_t ldx, const double* Y,
+                                   int64_t ldy, double beta, double* C, int64_t ldc, int flags, int nch);
+
 // One distributed product  C <- beta*C + alpha * X^T Y  (all matrices are windows of cyclically distributed globals;
 // local windows: X: k x m, Y: k x n, C: m x n).  X and Y are the LOCAL windows of this rank; the blocks actually
 // multiplied are the ones owned by (y,z,z) and (x,z,z).
@@ -146,6 +160,8 @@ capital_status_t product(Dist& D, int64_t m, int64_t n, int64_t k, double alpha,
   capital_ctx* ctx = D.ctx;
   const capital_grid_t& g = D.g;
   const int d = g.d, c = g.c, me = g.rank;
+  if (ctx->dist_pipeline && ctx->comm_stream && n >= 2048 && m >= 1024 && k >= 1024)
+    return product_pipelined(D, m, n, k, alpha, X, ldx, Y, ldy, beta, C, ldc, flags, 4);
   // The contraction index splits into d owner classes (k mod d = kb); the c layers share them: layer z takes the classes
   // kb = z (mod c) when c <= d (the reference has c == d: exactly one class per layer, summa.hpp:185-193), and when
   // c > d (2 x 1 x 1) the single class is cut into c/d row chunks of the local window.
@@ -198,6 +214,121 @@ capital_status_t product(Dist& D, int64_t m, int64_t n, int64_t k, double alpha,
   axpby_kernel<<<grid_for(ctx, m * n), 256, 0, D.st>>>(m, n, D.bufP, ldp, beta, C, ldc, (flags & CAPITAL_GEMM_C_UPPER) ? 1 : 0);
   ctx->counters.kernel_launches++;
   CAP_CUDA(cudaGetLastError());
+  return CAPITAL_OK;
+}
+
+capital_status_t comm_event(capital_ctx* ctx, cudaEvent_t* e) {
+  if (ctx->comm_used == ctx->comm_pool.size()) {
+    cudaEvent_t ev;
+    CAP_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    ctx->comm_pool.push_back(ev);
+  }
+  *e = ctx->comm_pool[ctx->comm_used++];
+  return CAPITAL_OK;
+}
+
+// Same product, software-pipelined over column chunks of the output so that the transfers hide behind the DMMA work
+// (the reference issues Bcast / GEMM / Allreduce strictly one after the other; its num_chunks option only chunks the
+// communication, summa.hpp:195-249).  Two streams: NCCL traffic on ctx->comm_stream, compute on D.st, joined by events:
+//     comm:     X | Y_0 | Y_1 | ... | Y_{c-1} |        AR_0 | AR_1 | ...
+//     compute:       wait X,Y_0: G_0 | wait Y_1: G_1 | ...        wait AR_0: C_0 | ...
+// Only the fetch of X and Y_0 and the last all-reduce stay exposed.
+capital_status_t product_pipelined(Dist& D, int64_t m, int64_t n, int64_t k, double alpha, const double* X, int64_t ldx, const double* Y,
+                                   int64_t ldy, double beta, double* C, int64_t ldc, int flags, int nch) {
+  capital_ctx* ctx = D.ctx;
+  const capital_grid_t& g = D.g;
+  const int d = g.d, c = g.c, me = g.rank;
+  cudaStream_t CS = D.st, NS = ctx->comm_stream;
+  ctx->comm_used = 0;
+  const int nslices = c > d ? c : d;
+  const int nchunk = c > d ? c / d : 1;
+  const int64_t ldp = packed_ld(m);
+  const int64_t cw = round_up(ceil_div(n, nch), 64);  // chunk width (columns)
+  const int nc_eff = (int)ceil_div(n, cw);
+  std::vector<cudaEvent_t> e_g(nc_eff, nullptr);
+  if (flags & CAPITAL_GEMM_C_UPPER) CAP_CUDA(cudaMemsetAsync(D.bufP, 0, (size_t)ldp * n * 8, CS));
+  bool first = true;
+  int last_slice = -1;
+  for (int sl = g.z; sl < nslices; sl += c) last_slice = sl;
+  for (int sl = g.z; sl < nslices; sl += c) {
+    const int kb = sl % d, chunk = sl / d;
+    int64_t r0 = 0, r1 = k;
+    int fl = flags;
+    if (nchunk > 1) {
+      r0 = (k * chunk / nchunk) & ~(int64_t)1;
+      r1 = chunk + 1 == nchunk ? k : ((k * (chunk + 1) / nchunk) & ~(int64_t)1);
+      fl &= CAPITAL_GEMM_C_UPPER;
+    }
+    const int64_t kk = r1 - r0;
+    if (kk <= 0) continue;
+    const int64_t ldk = packed_ld(kk);
+    const int srcX = rank_of(g, g.y, kb, g.z), srcY = rank_of(g, g.x, kb, g.z);
+    const bool iAmSrc = (g.y == kb);
+    const double* Xuse = X + r0; int64_t ldxu = ldx;
+    const double* Yuse = Y + r0; int64_t ldyu = ldy;
+    double* sendX = D.bufS;
+    double* sendY = D.bufS + ldk * (m > n ? m : n);
+    bool needSendX = false, needSendY = false;
+    if (iAmSrc) for (int t = 0; t < d; t++) { if (rank_of(g, t, g.x, g.z) != me) needSendX = true; if (rank_of(g, g.x, t, g.z) != me) needSendY = true; }
+    if (needSendX) CAP_TRY(copy_block(ctx, CS, kk, m, X + r0, ldx, sendX, ldk));
+    if (needSendY) CAP_TRY(copy_block(ctx, CS, kk, n, Y + r0, ldy, sendY, ldk));
+    // comm stream may start once the staging copies are done and the previous users of bufX / bufY (earlier GEMMs on CS) are finished
+    cudaEvent_t e_pack, e_x;
+    CAP_TRY(comm_event(ctx, &e_pack));
+    CAP_CUDA(cudaEventRecord(e_pack, CS));
+    CAP_CUDA(cudaStreamWaitEvent(NS, e_pack, 0));
+    const bool anyX = needSendX || srcX != me, anyY = needSendY || srcY != me;
+    if (anyX) {
+      CAP_NCCL(nccl().GroupStart());
+      if (iAmSrc) for (int t = 0; t < d; t++) { const int dx = rank_of(g, t, g.x, g.z); if (dx != me) CAP_NCCL(nccl().Send(sendX, (size_t)ldk * m, ncclFloat64, dx, D.world, NS)); }
+      if (srcX != me) { CAP_NCCL(nccl().Recv(D.bufX, (size_t)ldk * m, ncclFloat64, srcX, D.world, NS)); Xuse = D.bufX; ldxu = ldk; }
+      CAP_NCCL(nccl().GroupEnd());
+    }
+    CAP_TRY(comm_event(ctx, &e_x));
+    CAP_CUDA(cudaEventRecord(e_x, NS));
+    if (srcY != me) { Yuse = D.bufY; ldyu = ldk; }
+    std::vector<cudaEvent_t> e_y(nc_eff, nullptr);
+    for (int j = 0; j < nc_eff; j++) {
+      const int64_t c0 = (int64_t)j * cw, nc = (c0 + cw <= n) ? cw : n - c0;
+      if (anyY) {
+        CAP_NCCL(nccl().GroupStart());
+        if (iAmSrc) for (int t = 0; t < d; t++) { const int dy = rank_of(g, g.x, t, g.z); if (dy != me) CAP_NCCL(nccl().Send(sendY + c0 * ldk, (size_t)ldk * nc, ncclFloat64, dy, D.world, NS)); }
+        if (srcY != me) CAP_NCCL(nccl().Recv(D.bufY + c0 * ldk, (size_t)ldk * nc, ncclFloat64, srcY, D.world, NS));
+        CAP_NCCL(nccl().GroupEnd());
+      }
+      CAP_TRY(comm_event(ctx, &e_y[j]));
+      CAP_CUDA(cudaEventRecord(e_y[j], NS));
+    }
+    CAP_CUDA(cudaStreamWaitEvent(CS, e_x, 0));
+    for (int j = 0; j < nc_eff; j++) {
+      const int64_t c0 = (int64_t)j * cw, nc = (c0 + cw <= n) ? cw : n - c0;
+      CAP_CUDA(cudaStreamWaitEvent(CS, e_y[j], 0));
+      CAP_TRY(gemm_tn_off(ctx, CS, m, nc, kk, alpha, Xuse, ldxu, Yuse + c0 * ldyu, ldyu, first ? 0.0 : 1.0, D.bufP + c0 * ldp, ldp, fl, 0, (int)c0));
+      if (sl == last_slice && c > 1) {
+        CAP_TRY(comm_event(ctx, &e_g[j]));
+        CAP_CUDA(cudaEventRecord(e_g[j], CS));
+      }
+    }
+    first = false;
+  }
+  if (first) CAP_CUDA(cudaMemsetAsync(D.bufP, 0, (size_t)ldp * n * 8, CS));
+  const int up = (flags & CAPITAL_GEMM_C_UPPER) ? 1 : 0;
+  for (int j = 0; j < nc_eff; j++) {
+    const int64_t c0 = (int64_t)j * cw, nc = (c0 + cw <= n) ? cw : n - c0;
+    if (c > 1) {
+      if (e_g[j]) CAP_CUDA(cudaStreamWaitEvent(NS, e_g[j], 0));
+      else { cudaEvent_t e; CAP_TRY(comm_event(ctx, &e)); CAP_CUDA(cudaEventRecord(e, CS)); CAP_CUDA(cudaStreamWaitEvent(NS, e, 0)); }
+      CAP_NCCL(nccl().AllReduce(D.bufP + c0 * ldp, D.bufP + c0 * ldp, (size_t)ldp * nc, ncclFloat64, ncclSum, D.depth, NS));
+      cudaEvent_t e_r;
+      CAP_TRY(comm_event(ctx, &e_r));
+      CAP_CUDA(cudaEventRecord(e_r, NS));
+      CAP_CUDA(cudaStreamWaitEvent(CS, e_r, 0));
+    }
+    // C chunk = beta * C + P chunk; for upper-only outputs the mask row <= col uses the global column index
+    axpby_off_kernel<<<grid_for(ctx, m * nc), 256, 0, CS>>>(m, nc, D.bufP + c0 * ldp, ldp, beta, C + c0 * ldc, ldc, up, c0);
+    ctx->counters.kernel_launches++;
+    CAP_CUDA(cudaGetLastError());
+  }
   return CAPITAL_OK;
 }
 
@@ -315,6 +446,8 @@ extern "C" capital_status_t capital_comm_init(capital_ctx* ctx, const void* uid)
   CAP_NCCL(nccl().CommSplit(world, g.z, g.y * g.d + g.x, &slice, nullptr));
   ctx->comm_depth = depth;
   ctx->comm_slice = slice;
+  CAP_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+  if (const char* e = getenv("CAPITAL_DIST_PIPELINE")) ctx->dist_pipeline = atoi(e) != 0;
   return CAPITAL_OK;
 }
 
@@ -324,6 +457,9 @@ void dist_destroy(capital_ctx* ctx) {
   if (ctx->comm_slice) nccl().CommDestroy((ncclComm_t)ctx->comm_slice);
   if (ctx->comm_world) nccl().CommDestroy((ncclComm_t)ctx->comm_world);
   ctx->comm_depth = ctx->comm_slice = ctx->comm_world = nullptr;
+  if (ctx->comm_stream) { cudaStreamDestroy(ctx->comm_stream); ctx->comm_stream = nullptr; }
+  for (cudaEvent_t e : ctx->comm_pool) cudaEventDestroy(e);
+  ctx->comm_pool.clear();
 }
 
 capital_status_t dist_cholinv_factor(capital_ctx* ctx, const double* A_local, int64_t n, const capital_cholinv_args_t* args,

@@ -23,6 +23,7 @@ struct GemmParams {
   int M, N, K;
   int rowoffA, rowoffB;  // element offset of the operand's first row inside its (16B-aligned) tensor map
   int flags;
+  int noff;    // column index of this window of B / C inside the full operand (column-chunked launches)
   int koff;    // row index of this window inside the full operand (k-chunked launches keep the triangular k ranges right)
   int ksplit;  // gridDim.z chunks of the k range; > 1 => epilogue accumulates with atomics (C pre-initialised, beta ignored)
   double alpha, beta;
@@ -82,13 +83,14 @@ __global__ void __launch_bounds__(((BM / WM) * (BN / WN) + 4) * 32, MINB)
   const int tm = (flags & CAPITAL_GEMM_A_UPPER) ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
   const int tn = (flags & CAPITAL_GEMM_B_UPPER) ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
   const int m0 = tm * BM, n0 = tn * BN;
-  if ((flags & CAPITAL_GEMM_C_UPPER) && m0 > n0 + BN - 1) return;  // tile strictly below the diagonal
+  const int n0g = n0 + p.noff;  // column position used by the structure tests
+  if ((flags & CAPITAL_GEMM_C_UPPER) && m0 > n0g + BN - 1) return;  // tile strictly below the diagonal
 
   int kb = 0, ke = p.K;
   if (flags & CAPITAL_GEMM_A_UPPER) ke = min(ke, m0 + BM - p.koff);
   if (flags & CAPITAL_GEMM_A_LOWER) kb = max(kb, m0 - p.koff);
-  if (flags & CAPITAL_GEMM_B_UPPER) ke = min(ke, n0 + BN - p.koff);
-  if (flags & CAPITAL_GEMM_B_LOWER) kb = max(kb, n0 - p.koff);
+  if (flags & CAPITAL_GEMM_B_UPPER) ke = min(ke, n0g + BN - p.koff);
+  if (flags & CAPITAL_GEMM_B_LOWER) kb = max(kb, n0g - p.koff);
   kb &= ~(BK - 1);
   int nk = ke > kb ? (ke - kb + BK - 1) / BK : 0;
   if (nk == 0 && p.beta == 1.0 && p.ksplit <= 1) return;  // nothing to add (k-chunk entirely outside the operand's triangle)
@@ -186,7 +188,7 @@ __global__ void __launch_bounds__(((BM / WM) * (BN / WN) + 4) * 32, MINB)
 #pragma unroll
       for (int i = 0; i < FM; i++) {
         const int row = m0 + wm * WM + i * 8 + g;
-        if (row >= p.M || (upper_only && row > col)) continue;
+        if (row >= p.M || (upper_only && row > col + p.noff)) continue;
         double v = alpha * acc[i][j][e];
         if (p.ksplit > 1) { atomicAdd(cc + row, v); continue; }
         if (beta != 0.0) v += beta * cc[row];
@@ -225,14 +227,14 @@ capital_status_t make_map(capital_ctx* ctx, CUtensorMap* map, const double* base
 
 template <class Cfg, int BM, int BN>
 capital_status_t launch(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
-                        int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags, int ksplit, int koff = 0) {
+                        int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags, int ksplit, int koff = 0, int noff = 0) {
   static bool attr_set = false;
   if (!attr_set) {
     CAP_CUDA(cudaFuncSetAttribute(Cfg::kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem));
     attr_set = true;
   }
   GemmParams p;
-  p.M = (int)m; p.N = (int)n; p.K = (int)k; p.flags = flags; p.alpha = alpha; p.beta = beta; p.C = C; p.ldc = ldc; p.ksplit = ksplit; p.koff = koff;
+  p.M = (int)m; p.N = (int)n; p.K = (int)k; p.flags = flags; p.alpha = alpha; p.beta = beta; p.C = C; p.ldc = ldc; p.ksplit = ksplit; p.koff = koff; p.noff = noff;
   // TMA fetches 16-byte granules: a window that starts on an odd row (8-byte aligned only) cannot be addressed by
   // box coordinates, so it is first copied to an aligned scratch (O(k m) bytes against O(k m n) flops; only odd
   // split points of non-power-of-two sizes ever take this path).
@@ -291,7 +293,7 @@ capital_status_t gemm_tn_chunked(capital_ctx* ctx, cudaStream_t st, int64_t m, i
   if (kc <= 0 || k <= kc + kc / 2) return gemm_tn(ctx, st, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags);
   for (int64_t k0 = 0; k0 < k; k0 += kc) {
     const int64_t kk = (k - k0 < kc + kc / 2) ? k - k0 : kc;
-    CAP_TRY(gemm_tn_off(ctx, st, m, n, kk, alpha, A + k0, lda, B + k0, ldb, k0 == 0 ? beta : 1.0, C, ldc, flags, (int)k0));
+    CAP_TRY(gemm_tn_off(ctx, st, m, n, kk, alpha, A + k0, lda, B + k0, ldb, k0 == 0 ? beta : 1.0, C, ldc, flags, (int)k0, 0));
     if (kk != kc) break;
   }
   return CAPITAL_OK;
@@ -299,11 +301,11 @@ capital_status_t gemm_tn_chunked(capital_ctx* ctx, cudaStream_t st, int64_t m, i
 
 capital_status_t gemm_tn(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
                          int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags) {
-  return gemm_tn_off(ctx, st, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags, 0);
+  return gemm_tn_off(ctx, st, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags, 0, 0);
 }
 
 capital_status_t gemm_tn_off(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
-                             int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags, int koff) {
+                             int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags, int koff, int noff) {
   if (m <= 0 || n <= 0) return CAPITAL_OK;
   if (k < 0 || lda < k || ldb < k || ldc < m || (lda & 1) || (ldb & 1) || ((uintptr_t)A & 7) || ((uintptr_t)B & 7)) {
     ctx->set_error("gemm_tn: invalid/unsupported leading dimensions (lda, ldb must be even and >= k)");
@@ -329,12 +331,12 @@ capital_status_t gemm_tn_off(capital_ctx* ctx, cudaStream_t st, int64_t m, int64
       CAP_TRY(ctx->prof_event(&e0)); CAP_TRY(ctx->prof_event(&e1));
       CAP_CUDA(cudaEventRecord(e0, st));
     }
-    CAP_TRY((launch<CfgBig, 128, 128>(ctx, st, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags, 1, koff)));
+    CAP_TRY((launch<CfgBig, 128, 128>(ctx, st, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags, 1, koff, noff)));
     if (ctx->profiling) {
       CAP_CUDA(cudaEventRecord(e1, st));
       ctx->prof_recs.push_back({e0, e1, f});
     }
     return CAPITAL_OK;
   }
-  return launch<CfgSmall, 64, 64>(ctx, st, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags, 1, koff);
+  return launch<CfgSmall, 64, 64>(ctx, st, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags, 1, koff, noff);
 }

@@ -63,7 +63,8 @@ def main():
         c = 2 if world == 2 else 1
         topo = cb.topo.square(world, rank, c)
         d = topo.d
-        for n, ci, bcm in ((512, 1, -2), (2048, 0, -3), (3072, 1, -3)):
+        sizes = ((512, 1, -2), (2048, 0, -3), (3072, 1, -3)) + (((8192, 1, -4),) if os.environ.get("CAPITAL_DIST_PIPELINE") else ())
+        for n, ci, bcm in sizes:
             A = cb.matrix(n, n, d, d).distribute_symmetric(topo)
             args = cb.cholinv.info(ci, 1, bcm, "U")
             cb.cholinv.factor(A, args, topo)
