@@ -193,6 +193,8 @@ capital_status_t capital_create(capital_ctx** out, const capital_grid_t* grid, i
   if (!ok) { capital_destroy(ctx); return CAPITAL_ERR_CUDA; }
   ctx->encode = (cuTensorMapEncodeTiled_fn)fn;
   if (const char* e = getenv("CAPITAL_KCHUNK")) ctx->kchunk = atoll(e);
+  if (const char* e = getenv("CAPITAL_FAR_MIN")) ctx->far_min = atoll(e);
+  if (const char* e = getenv("CAPITAL_SIDE_MIN")) ctx->side_min = atoll(e);
   *out = ctx;
   return CAPITAL_OK;
 }

@@ -95,7 +95,7 @@ capital_status_t rec(Rec& r, int64_t o, int64_t n, bool complete, cudaEvent_t pe
   // "trsm" via the inverse (cholinv.hpp:116-122): R12 = Rinv11^T A12
   CAP_TRY(gemm_tn(ctx, r.M, s1, s2, s1, 1.0, Ri, ldri, W12, ldw, 0.0, R12, ldr, CAPITAL_GEMM_A_UPPER));
   cudaEvent_t e_r12 = nullptr, e_tt = nullptr, e_far = nullptr;
-  const bool use_side = r.S != nullptr && s1 >= 256;
+  const bool use_side = r.S != nullptr && s1 >= r.ctx->side_min;
   if (use_side) {
     CAP_TRY(new_event(ctx, &e_r12));
     CAP_CUDA(cudaEventRecord(e_r12, r.M));
@@ -151,7 +151,7 @@ capital_status_t cholinv_local(capital_ctx* ctx, cudaStream_t st, int64_t n, dou
     if (S) CAP_CUDA(cudaStreamWaitEvent(S, e_in, 0));
   }
   const bool aligned = ((((uintptr_t)W | (uintptr_t)R | (uintptr_t)Ri | (uintptr_t)RiT) & 15) == 0) && !((ldw | ldr | ldri | ldrit) & 1);
-  Rec r{ctx, M, S, W, R, Ri, RiT, ldw, ldr, ldri, ldrit, bc, split, hooks, 2048, n, ctx->kchunk, aligned};
+  Rec r{ctx, M, S, W, R, Ri, RiT, ldw, ldr, ldri, ldrit, bc, split, hooks, ctx->far_min, n, ctx->kchunk, aligned};
   CAP_TRY(rec(r, 0, n, complete_top, nullptr, 0));
   if (M != st) {
     if (S) {  // join the deferred stream (all its work has been consumed through events, this is just the fence)

@@ -75,6 +75,8 @@ struct capital_ctx {
   struct ProfRec { cudaEvent_t e0, e1; double flops; };
   bool profiling = false;
   int64_t kchunk = 0;       // k-chunking of deferred GEMMs (env CAPITAL_KCHUNK); measured r01: 0 (off) is fastest, see profiles/r01c_notes.md
+  int64_t far_min = 2048;   // trailing updates at least this large are split into near (critical) / far (deferred)   [env CAPITAL_FAR_MIN]
+  int64_t side_min = 1024;  // nodes whose left part is at least this large defer T^T to the low-priority stream      [env CAPITAL_SIDE_MIN]; swept in r01: 256 -> 68.9 ms, 1024 -> 67.0 ms
   bool no_overlap = false;  // debug / measurement: run the recursion on one stream
   std::vector<cudaEvent_t> prof_pool;
   size_t prof_used = 0;

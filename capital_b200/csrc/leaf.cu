@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include <cooperative_groups.h>
 #include <stdlib.h>
+#include <type_traits>
 namespace cg = cooperative_groups;
 
 namespace {
@@ -239,34 +240,60 @@ __device__ __forceinline__ void tile_store_from_rowmajor(double* __restrict__ ds
 // reciprocal square root is an FP32 seed + two FP64 Newton steps: ~200 cycles per pivot, no barrier in the chain.
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
+// compile-time loop: register arrays must only ever be indexed by constants (a loop the unroller leaves rolled would push
+// them to local memory)
+template <int I, int END, int STEP = 1, typename F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < END) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + STEP, END, STEP>(f);
+  }
+}
+
 // c[i] = A(i, lane) (upper part meaningful) -> R written to sRb (element (i, j) at sRb[j * TLD + i]), x[i] = Rinv(i, lane).
-// ub: 64 doubles of shared scratch (the scaled pivot row is broadcast through it: one conflict-free store and
+// ub: 128 doubles of shared scratch (the scaled pivot row is broadcast through it: one conflict-free store and
 // pipelined broadcast loads per pivot instead of 2 x 31 dependent shuffles).  The next pivot's rsqrt is started as
 // soon as its diagonal entry is final, so it overlaps with the rest of the rank-1 update.
 __device__ __forceinline__ void warp_potrf_trtri_32(double (&c)[32], double (&x)[32], double* __restrict__ sRb, double* __restrict__ ub,
                                                     int lane, int* info, int pivot_base, long long* dbg2) {
   double myrs = 0.0;
   if (dbg2 && lane == 0) dbg2[0] = clock64();
-  double d = shfl_d(c[0], 0);
-  if (!(d > 0.0)) { if (lane == 0) atomicCAS(info, 0, pivot_base + 1); d = 1.0; }
-  double rs = fast_rsqrt(d);
-#pragma unroll
-  for (int k = 0; k < 32; k++) {
-    const double u = (lane > k) ? c[k] * rs : (lane == k ? d * rs : 0.0);  // R(k, lane)
-    c[k] = u;
-    if (lane == k) myrs = rs;
-    double* row = ub + (k & 1) * 32;
-    row[lane] = u;
+  // Two pivots per step.  With a = A(k,k), l = A(k,k+1), b = A(k+1,k+1) the second pivot is det / a, det = a b - l^2, so
+  // rsqrt(a) and rsqrt(det) are independent and overlap: one rsqrt latency per TWO pivots on the chain.
+  //   R(k,k) = a ra          R(k,j)   = A(k,j) ra                       (ra = 1/sqrt(a))
+  //   R(k+1,k+1) = det rdet ra         R(k+1,j) = (A(k+1,j) - l ra R(k,j)) sqrt(a) rdet   (rdet = 1/sqrt(det))
+  double a = shfl_d(c[0], 0), l = shfl_d(c[0], 1), b = shfl_d(c[1], 1);
+  static_for<0, 32, 2>([&](auto kc) {
+    constexpr int k = decltype(kc)::value;
+    if (!(a > 0.0)) { if (lane == k) atomicCAS(info, 0, pivot_base + k + 1); a = 1.0; }
+    double det = fma(b, a, -(l * l));
+    if (!(det > 0.0)) { if (lane == k + 1) atomicCAS(info, 0, pivot_base + k + 2); det = 1.0; }
+    const double ra = fast_rsqrt(a), rdet = fast_rsqrt(det);
+    const double sa = a * ra, lk = l * ra, rs2 = sa * rdet;
+    const double u0 = (lane > k) ? c[k] * ra : (lane == k ? sa : 0.0);                                  // R(k, lane)
+    const double t1 = fma(-lk, u0, c[k + 1]);
+    const double u1 = (lane > k + 1) ? t1 * rs2 : (lane == k + 1 ? det * rdet * ra : 0.0);            // R(k+1, lane)
+    c[k] = u0;
+    c[k + 1] = u1;
+    if (lane == k) myrs = ra;
+    if (lane == k + 1) myrs = rs2;
+    double* row0 = ub + (k & 2) * 32;
+    double* row1 = row0 + 32;
+    row0[lane] = u0;
+    row1[lane] = u1;
     __syncwarp();
-    if (k < 31) {
-      c[k + 1] = fma(-row[k + 1], u, c[k + 1]);
-      d = shfl_d(c[k + 1], k + 1);  // next pivot: final already
-      if (!(d > 0.0)) { if (lane == k + 1) atomicCAS(info, 0, pivot_base + k + 2); d = 1.0; }
-      rs = fast_rsqrt(d);
-#pragma unroll
-      for (int i = k + 2; i < 32; i++) c[i] = fma(-row[i], u, c[i]);  // A(i, lane) -= R(k, i) R(k, lane)
+    if constexpr (k + 2 < 32) {
+      c[k + 2] = fma(-row1[k + 2], u1, fma(-row0[k + 2], u0, c[k + 2]));
+      c[k + 3] = fma(-row1[k + 3], u1, fma(-row0[k + 3], u0, c[k + 3]));
+      a = shfl_d(c[k + 2], k + 2);  // next pair: final already
+      l = shfl_d(c[k + 2], k + 3);
+      b = shfl_d(c[k + 3], k + 3);
+      static_for<k + 4, 32>([&](auto ic) {  // rank-2 update of column `lane`
+        constexpr int i = decltype(ic)::value;
+        c[i] = fma(-row1[i], u1, fma(-row0[i], u0, c[i]));
+      });
     }
-  }
+  });
   if (dbg2 && lane == 0) dbg2[1] = clock64();
 #pragma unroll
   for (int i = 0; i < 32; i++) {
@@ -566,7 +593,7 @@ capital_status_t leaf_cholinv(capital_ctx* ctx, cudaStream_t st, int nb, const d
 capital_status_t basecase_cholinv(capital_ctx* ctx, cudaStream_t st, int nb, double* W, int64_t ldw, double* R, int64_t ldr, double* Ri,
                                   int64_t ldri, double* RiT, int64_t ldrit) {
   if (nb % 64 != 0 || nb < 64 || nb > BASECASE_MAX || RiT == nullptr) return CAPITAL_ERR_INVALID;
-  constexpr int smem = (4 * TILE_DOUBLES + 64) * (int)sizeof(double);
+  constexpr int smem = (4 * TILE_DOUBLES + 128) * (int)sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
     CAP_CUDA(cudaFuncSetAttribute(basecase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
