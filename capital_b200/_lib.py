@@ -16,7 +16,7 @@ EXPORTS = [  # every symbol include/capital_b200.h declares
     "capital_comm_unique_id", "capital_comm_init", "capital_destroy", "capital_last_error", "capital_get_counters",
     "capital_reset_counters", "capital_synchronize", "capital_last_factor_ms", "capital_profile_begin", "capital_profile_end", "capital_set_overlap", "capital_distribute_symmetric_f64",
     "capital_distribute_random_f64", "capital_cholinv_factor_f64", "capital_cholinv_residual_f64",
-    "capital_cacqr_factor_f64", "capital_cacqr_residual_f64", "capital_blas_gemm_tn_f64",
+    "capital_cacqr_factor_f64", "capital_cacqr_residual_f64", "capital_summa_gemm_tn_f64", "capital_blas_gemm_tn_f64",
     "capital_lapack_potrf_trtri_f64",
 ]
 
@@ -75,6 +75,7 @@ def lib() -> C.CDLL:
     L.capital_cholinv_residual_f64.argtypes = [vp, vp, i64, ci, vp, C.POINTER(dbl)]
     L.capital_cacqr_factor_f64.argtypes = [vp, vp, i64, i64, ci, C.POINTER(CholinvArgs), ci, vp, vp]
     L.capital_cacqr_residual_f64.argtypes = [vp, vp, i64, i64, vp, ci, vp, C.POINTER(dbl), C.POINTER(dbl)]
+    L.capital_summa_gemm_tn_f64.argtypes = [vp, i64, i64, i64, dbl, vp, vp, dbl, vp]
     L.capital_blas_gemm_tn_f64.argtypes = [vp, i64, i64, i64, dbl, vp, i64, vp, i64, dbl, vp, i64, ci]
     L.capital_lapack_potrf_trtri_f64.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64]
     for name in EXPORTS:

@@ -437,6 +437,14 @@ capital_status_t capital_cacqr_residual_f64(capital_ctx* ctx, const double* A_lo
   return dist_cacqr_residual(ctx, A_local, m, n, Q_local, rstruct, R_local, residual, orthogonality);
 }
 
+// ---- SUMMA -----------------------------------------------------------------------------------
+capital_status_t capital_summa_gemm_tn_f64(capital_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha, const double* A_local,
+                                           const double* B_local, double beta, double* C_local) {
+  if (!ctx || !A_local || !B_local || !C_local || m <= 0 || n <= 0 || k <= 0) return CAPITAL_ERR_INVALID;
+  CAP_CUDA(cudaSetDevice(ctx->device));
+  return dist_summa_gemm_tn(ctx, m, n, k, alpha, A_local, B_local, beta, C_local);
+}
+
 // ---- leaf-engine seam -------------------------------------------------------------------------
 capital_status_t capital_blas_gemm_tn_f64(capital_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
                                           const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags) {

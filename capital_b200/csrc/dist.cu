@@ -554,6 +554,54 @@ capital_status_t dist_cholinv_residual(capital_ctx* ctx, const double* A_local, 
   return CAPITAL_OK;
 }
 
+capital_status_t dist_summa_gemm_tn(capital_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha, const double* A_local,
+                                    const double* B_local, double beta, double* C_local) {
+  const capital_grid_t& g = ctx->grid;
+  CAP_TRY(need_comm(ctx));
+  if ((g.c % g.d != 0 && g.d % g.c != 0) || m % g.d || n % g.d || k % g.d) {
+    ctx->set_error("summa gemm: needs a grid with c | d or d | c, and d | m, n, k");
+    return CAPITAL_ERR_UNSUPPORTED;
+  }
+  const int64_t ml = m / g.d, nl = n / g.d, kl = k / g.d;
+  cudaStream_t st = ctx->stream;
+  const double *dA, *dB;
+  double* dC;
+  CAP_TRY(cap_stage_in(ctx, A_local, (size_t)kl * ml, "summa_A", &dA));
+  CAP_TRY(cap_stage_in(ctx, B_local, (size_t)kl * nl, "summa_B", &dB));
+  const bool c_host = !cap_is_device_ptr(C_local);
+  if (c_host) {
+    const double* tmp;
+    CAP_TRY(cap_stage_in(ctx, C_local, (size_t)ml * nl, "summa_C", &tmp));
+    dC = const_cast<double*>(tmp);
+  } else dC = C_local;
+  // TMA needs even leading dimensions: repack operands whose local row count is odd
+  const int64_t ldk = packed_ld(kl);
+  double *pA = const_cast<double*>(dA), *pB = const_cast<double*>(dB);
+  if (ldk != kl) {
+    CAP_TRY(ctx->workspace("summa_pA", (size_t)ldk * ml * 8, (void**)&pA));
+    CAP_TRY(ctx->workspace("summa_pB", (size_t)ldk * nl * 8, (void**)&pB));
+    CAP_TRY(copy_block(ctx, st, kl, ml, dA, kl, pA, ldk));
+    CAP_TRY(copy_block(ctx, st, kl, nl, dB, kl, pB, ldk));
+  }
+  if (g.size == 1) {
+    CAP_TRY(gemm_tn(ctx, st, ml, nl, kl, alpha, pA, ldk, pB, ldk, beta, dC, ml, 0));
+  } else {
+    Dist D{ctx, st, g};
+    D.L = 0; D.ld = 0; D.split = 1; D.bc_local = 0;
+    D.world = (ncclComm_t)ctx->comm_world; D.depth = (ncclComm_t)ctx->comm_depth; D.slice = (ncclComm_t)ctx->comm_slice;
+    const int64_t mx = ml > nl ? ml : nl;
+    const size_t blk = (size_t)packed_ld(kl > ml ? kl : ml) * mx * 8 + 4096;
+    CAP_TRY(ctx->workspace("xferX", blk, (void**)&D.bufX));
+    CAP_TRY(ctx->workspace("xferY", blk, (void**)&D.bufY));
+    CAP_TRY(ctx->workspace("xferP", blk, (void**)&D.bufP));
+    CAP_TRY(ctx->workspace("xferS", 2 * blk, (void**)&D.bufS));
+    CAP_TRY(product(D, ml, nl, kl, alpha, pA, ldk, pB, ldk, beta, dC, ml, 0));
+  }
+  if (c_host) CAP_TRY(cap_stage_out_end(ctx, C_local, (size_t)ml * nl, dC));
+  CAP_CUDA(cudaStreamSynchronize(st));
+  return CAPITAL_OK;
+}
+
 // ---- CholeskyQR2, 1D --------------------------------------------------------------------------------------------
 namespace {
 struct Qr {

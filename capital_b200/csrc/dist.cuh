@@ -12,6 +12,9 @@ capital_status_t dist_cacqr_factor(capital_ctx* ctx, const double* A_local, int6
 capital_status_t dist_cacqr_residual(capital_ctx* ctx, const double* A_local, int64_t m, int64_t n, const double* Q_local,
                                      capital_structure_t rstruct, const double* R_local, double* residual, double* orthogonality);
 
+capital_status_t dist_summa_gemm_tn(capital_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha, const double* A_local,
+                                    const double* B_local, double beta, double* C_local);
+
 // helpers shared with api.cu
 bool cap_is_device_ptr(const void* p);
 capital_status_t cap_stage_in(capital_ctx* ctx, const double* src, size_t count, const char* name, const double** out);

@@ -130,6 +130,14 @@ capital_status_t capital_cacqr_residual_f64(capital_ctx* ctx, const double* A_lo
                                             const double* Q_local, capital_structure_t r_structure,
                                             const double* R_local, double* residual, double* orthogonality);
 
+/* ---- SUMMA ------------------------------------------------------------------------------------ */
+/* matmult::summa::invoke(A, B, C, topo, gemm{Trans, NoTrans, alpha, beta}) -- summa.hpp:6-44 in the T*N form the validators
+ * and syrk_internal use (test/cholesky/validate.hpp:35, summa.hpp:143-145):  C = alpha * A^T B + beta * C  with A (k x m),
+ * B (k x n), C (m x n) all element-cyclic over the d x d face (local blocks k/d x m/d, k/d x n/d, m/d x n/d, column-major,
+ * replicated over the c layers; d must divide m, n, k).  Host or device pointers. */
+capital_status_t capital_summa_gemm_tn_f64(capital_ctx* ctx, int64_t m_global, int64_t n_global, int64_t k_global, double alpha,
+                                           const double* A_local, const double* B_local, double beta, double* C_local);
+
 /* ---- leaf-engine seam (the reference's designated swap point, blas/engine.h:7-8) ------------- */
 /* blas::engine::_gemm (blas/interface.hpp:43-59) restricted to the T*N form the hot path executes
  * (summa.hpp:143-145): C[m x n] = alpha * A^T B + beta * C, A is k x m, B is k x n, all column-major

@@ -77,6 +77,21 @@ def main():
             res = cb.cholinv.residual(A, args, topo)
             ok &= er < 2e-13 and ei < 2e-13 and res < 1e-12
             msgs.append(f"grid {c}x{d}x{d} n={n} ci={ci}: dR={er:.1e} dRinv={ei:.1e} res={res:.1e}")
+    if world in (2, 4, 8):
+        # --- SUMMA GEMM entry point (T*N) on the same grid, against the global product ---
+        c = {2: 2, 4: 1, 8: 2}[world]
+        topo = cb.topo.square(world, rank, c)
+        d = topo.d
+        m, n, k = 384, 256, 512
+        rng = np.random.default_rng(5)
+        Ag, Bg, Cg = rng.standard_normal((k, m)), rng.standard_normal((k, n)), rng.standard_normal((m, n))
+        mk = lambda G: cb.matrix(G.shape[1], G.shape[0], d, d, data=torch.from_numpy(np.asfortranarray(co.cyclic_local(G, d, d, topo.x, topo.y)).ravel(order="F").copy()).cuda())
+        A, B, C = mk(Ag), mk(Bg), mk(Cg)
+        cb.summa.invoke(A, B, C, topo, alpha=1.5, beta=-0.5)
+        ref = co.cyclic_local(1.5 * Ag.T @ Bg - 0.5 * Cg, d, d, topo.x, topo.y)
+        es = np.abs(C.view2d().cpu().numpy() - ref).max()
+        ok &= es < 1e-11
+        msgs.append(f"summa gemm {c}x{d}x{d}: err={es:.1e}")
     # --- 1D CholeskyQR2 on all ranks ---
     qt = cb.topo.rect(world, rank, 1)
     if world == 8:

@@ -131,3 +131,15 @@ def test_cacqr_matches_oracle(m, n, it):
     assert res < 1e-13
     assert orth < (1e-14 if it == 2 else 1e-12)
     assert abs(res - co.qr_residual(a, Q, R)) < 1e-15
+
+
+@pytest.mark.parametrize("m,n,k", [(256, 192, 320), (1000, 520, 777), (2048, 2048, 1024)])
+def test_summa_gemm_entry_point(topo, m, n, k):
+    """matmult::summa::invoke (T*N form) on the 1x1x1 grid against an FP64 torch reference."""
+    A = cb.matrix(m, k, 1, 1); B = cb.matrix(n, k, 1, 1); C = cb.matrix(n, m, 1, 1)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    for M in (A, B, C):
+        M.data.copy_(torch.rand(M.data.numel(), dtype=torch.float64, device="cuda", generator=g) - 0.5)
+    ref = 0.5 * (A.view2d().t() @ B.view2d()) - 2.0 * C.view2d()
+    cb.summa.invoke(A, B, C, topo, alpha=0.5, beta=-2.0)
+    assert (C.view2d() - ref).abs().max().item() < 1e-12
