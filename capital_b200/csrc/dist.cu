@@ -475,8 +475,6 @@ capital_status_t dist_cholinv_factor(capital_ctx* ctx, const double* A_local, in
   const size_t out_count = ostruct == CAPITAL_UPPERTRI_PACKED ? (size_t)L * (L + 1) / 2 : (size_t)L * L;
   cudaStream_t st = ctx->stream;
   CAP_CUDA(cudaEventRecord(ctx->ev_start, st));
-  const double* dA;
-  CAP_TRY(cap_stage_in(ctx, A_local, (size_t)L * L, "A_in", &dA));
   Dist D{ctx, st, g};
   D.L = L; D.ld = ld; D.split = (int)args->split;
   D.bc_local = capital_cholinv_bc_dimension(L, g.c, g.d, args->bc_mult_dim) / g.d;
@@ -498,7 +496,18 @@ capital_status_t dist_cholinv_factor(capital_ctx* ctx, const double* A_local, in
   CAP_CUDA(cudaMemsetAsync(D.Ri, 0, (size_t)ld * L * 8, st));
   CAP_CUDA(cudaMemsetAsync(D.RiT, 0, (size_t)ld * L * 8, st));
   CAP_CUDA(cudaMemsetAsync(D.R, 0, (size_t)ld * L * 8, st));
-  CAP_TRY(copy_block(ctx, st, L, L, dA, L, D.W, ld));
+  if (cap_is_device_ptr(A_local)) {
+    CAP_TRY(copy_block(ctx, st, L, L, A_local, L, D.W, ld));  // serialize(A -> R), cholinv.hpp:13
+  } else {
+    // host caller: only the (local) upper triangle is read, so only rows [0, column chunk end) travel
+    const int64_t chunk = round_up(ceil_div(L, 16), 64);
+    for (int64_t c0 = 0; c0 < L; c0 += chunk) {
+      const int64_t nc = (c0 + chunk <= L) ? chunk : L - c0, rows = c0 + nc;
+      CAP_CUDA(cudaMemcpy2DAsync(D.W + c0 * ld, (size_t)ld * 8, A_local + c0 * L, (size_t)L * 8, (size_t)rows * 8, (size_t)nc,
+                                 cudaMemcpyHostToDevice, st));
+      ctx->counters.h2d_bytes += rows * nc * 8;
+    }
+  }
   CAP_TRY(invoke(D, 0, L, args->complete_inv != 0));
   if (ostruct == CAPITAL_UPPERTRI_PACKED) {
     CAP_TRY(pack_upper(ctx, st, L, D.R, ld, dR, 0));
