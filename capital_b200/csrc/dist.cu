@@ -362,7 +362,8 @@ capital_status_t base_case(Dist& D, int64_t o, int64_t s) {
   CAP_TRY(ctx->workspace("bc_RiT", (size_t)ldb * b * 8, (void**)&dRiT));
   double* Wo = D.W + o * D.ld + o;
   CAP_TRY(copy_block(ctx, D.st, s, s, Wo, D.ld, D.bufS, lds));
-  CAP_NCCL(nccl().AllGather(D.bufS, gath, (size_t)lds * s, ncclFloat64, D.slice, D.st));  // policy.h:176
+  if (g.size == 1) CAP_CUDA(cudaMemcpyAsync(gath, D.bufS, (size_t)lds * s * 8, cudaMemcpyDeviceToDevice, D.st));
+  else CAP_NCCL(nccl().AllGather(D.bufS, gath, (size_t)lds * s, ncclFloat64, D.slice, D.st));  // policy.h:176
   blocks_to_dense_kernel<<<grid_for(ctx, b * b), 256, 0, D.st>>>((int)s, d, gath, lds, dW, ldb);
   ctx->counters.kernel_launches++;
   CAP_CUDA(cudaGetLastError());
@@ -641,13 +642,158 @@ capital_status_t sweep(Qr& q, double* Rout) {
 }
 }  // namespace
 
+// ---- CholeskyQR2, 3D grid (c == d) ---------------------------------------------------------------------------------
+// qr::cacqr::invoke_3d / sweep_3d (cacqr.hpp:75-120,195-215): Gram matrix by a SUMMA step, cholinv::factor on the n x n Gram
+// matrix over the same grid, Q <- Q R^{-1} by a SUMMA trmm.  Here each of those is the distributed A^T B product of this file:
+//   G    = Q^T Q                      product(X = Q, Y = Q)                   [row Bcast + dgemm + column Reduce + depth Bcast, :92-99]
+//   R, R^{-1} from invoke() on G                                                 [cholinv::factor, :103]
+//   Q^T <- R^{-T} Q^T                  product(X = Rinv (upper), Y = Q^T)      [summa trmm Right/Upper, :111]
+// with the global transposes done by the partner exchange (util::transpose).  The complete inverse is always formed
+// (the reference's block `solve` for complete_inv == 0, :44-73, yields the same Q).
+namespace {
+struct Qr3 {
+  Dist* D;
+  int64_t ml, nl, ldq, ldn;
+  double *Q, *T1, *T2;
+};
+capital_status_t sweep3d(Qr3& q, double* Rout) {
+  Dist& D = *q.D;
+  capital_ctx* ctx = D.ctx;
+  const int64_t ml = q.ml, nl = q.nl, ld = q.ldn;
+  CAP_TRY(product(D, nl, nl, ml, 1.0, q.Q, q.ldq, q.Q, q.ldq, 0.0, D.W, ld, 0));
+  CAP_CUDA(cudaMemsetAsync(D.Ri, 0, (size_t)ld * nl * 8, D.st));
+  CAP_CUDA(cudaMemsetAsync(D.RiT, 0, (size_t)ld * nl * 8, D.st));
+  CAP_CUDA(cudaMemsetAsync(D.R, 0, (size_t)ld * nl * 8, D.st));
+  CAP_TRY(invoke(D, 0, nl, true));
+  CAP_TRY(copy_block(ctx, D.st, nl, nl, D.R, ld, Rout, ld));
+  CAP_TRY(transpose_dist(D, ml, nl, q.Q, q.ldq, q.T1, ld));                                           // T1 = Q^T
+  CAP_TRY(product(D, nl, ml, nl, 1.0, D.Ri, ld, q.T1, ld, 0.0, q.T2, ld, CAPITAL_GEMM_A_UPPER));      // T2 = Rinv^T Q^T
+  CAP_TRY(transpose_dist(D, nl, ml, q.T2, ld, q.Q, q.ldq));                                           // Q = T2^T
+  return CAPITAL_OK;
+}
+capital_status_t qr3_setup(capital_ctx* ctx, Dist& D, Qr3& q, int64_t m, int64_t n, const capital_cholinv_args_t* ci_args) {
+  const capital_grid_t& g = ctx->grid;
+  if (m % g.d || n % g.d) {
+    ctx->set_error("cacqr 3D: d must divide m and n");
+    return CAPITAL_ERR_UNSUPPORTED;
+  }
+  q.D = &D;
+  q.ml = m / g.d; q.nl = n / g.d; q.ldq = round_up(q.ml, 16); q.ldn = round_up(q.nl, 16);
+  D.L = q.nl; D.ld = q.ldn; D.split = ci_args ? (int)ci_args->split : 1;
+  if (D.split <= 0) D.split = 1;
+  D.bc_local = capital_cholinv_bc_dimension(q.nl, g.c, g.d, ci_args ? ci_args->bc_mult_dim : 0) / g.d;
+  D.world = (ncclComm_t)ctx->comm_world; D.depth = (ncclComm_t)ctx->comm_depth; D.slice = (ncclComm_t)ctx->comm_slice;
+  const size_t nn = (size_t)q.ldn * q.nl * 8;
+  CAP_TRY(ctx->workspace("q3W", nn, (void**)&D.W));
+  CAP_TRY(ctx->workspace("q3R", nn, (void**)&D.R));
+  CAP_TRY(ctx->workspace("q3Ri", nn, (void**)&D.Ri));
+  CAP_TRY(ctx->workspace("q3RiT", nn, (void**)&D.RiT));
+  CAP_TRY(ctx->workspace("q3Q", (size_t)q.ldq * q.nl * 8, (void**)&q.Q));
+  CAP_TRY(ctx->workspace("q3T1", (size_t)q.ldn * q.ml * 8, (void**)&q.T1));
+  CAP_TRY(ctx->workspace("q3T2", (size_t)q.ldn * q.ml * 8, (void**)&q.T2));
+  const size_t blk = ((size_t)packed_ld(q.ml) * packed_ld(q.nl) + (size_t)packed_ld(q.nl) * packed_ld(q.nl)) * 8 + 4096;
+  CAP_TRY(ctx->workspace("xferX", blk, (void**)&D.bufX));
+  CAP_TRY(ctx->workspace("xferY", blk, (void**)&D.bufY));
+  CAP_TRY(ctx->workspace("xferP", blk, (void**)&D.bufP));
+  CAP_TRY(ctx->workspace("xferS", 2 * blk, (void**)&D.bufS));
+  return CAPITAL_OK;
+}
+capital_status_t cacqr3d_factor(capital_ctx* ctx, const double* A_local, int64_t m, int64_t n, int num_iter, const capital_cholinv_args_t* ci_args,
+                                capital_structure_t rstruct, double* Q_local, double* R_local) {
+  const capital_grid_t& g = ctx->grid;
+  cudaStream_t st = ctx->stream;
+  CAP_CUDA(cudaEventRecord(ctx->ev_start, st));
+  Dist D{ctx, st, g};
+  Qr3 q{};
+  CAP_TRY(qr3_setup(ctx, D, q, m, n, ci_args));
+  const int64_t ml = q.ml, nl = q.nl, ld = q.ldn;
+  const double* dA;
+  CAP_TRY(cap_stage_in(ctx, A_local, (size_t)ml * nl, "A_in", &dA));
+  const size_t r_count = rstruct == CAPITAL_UPPERTRI_PACKED ? (size_t)nl * (nl + 1) / 2 : (size_t)nl * nl;
+  double *dQ, *dR, *R1, *R2, *Rt, *Rf;
+  CAP_TRY(cap_stage_out_begin(ctx, Q_local, (size_t)ml * nl, "Q_out", &dQ));
+  CAP_TRY(cap_stage_out_begin(ctx, R_local, r_count, "R_out", &dR));
+  const size_t nn = (size_t)ld * nl * 8;
+  CAP_TRY(ctx->workspace("q3R1", nn, (void**)&R1));
+  CAP_TRY(ctx->workspace("q3R2", nn, (void**)&R2));
+  CAP_TRY(ctx->workspace("q3Rt", nn, (void**)&Rt));
+  CAP_TRY(ctx->workspace("q3Rf", nn, (void**)&Rf));
+  CAP_CUDA(cudaMemsetAsync(ctx->d_info, 0, sizeof(int), st));
+  CAP_TRY(copy_block(ctx, st, ml, nl, dA, ml, q.Q, q.ldq));
+  CAP_TRY(sweep3d(q, R1));
+  const double* Rfinal = R1;
+  if (num_iter > 1) {
+    CAP_TRY(sweep3d(q, R2));
+    CAP_TRY(transpose_dist(D, nl, nl, R2, ld, Rt, ld));  // R = R2 R1 = (R2^T)^T R1  (cacqr.hpp:207-209)
+    CAP_CUDA(cudaMemsetAsync(Rf, 0, nn, st));
+    CAP_TRY(product(D, nl, nl, nl, 1.0, Rt, ld, R1, ld, 0.0, Rf, ld, CAPITAL_GEMM_A_LOWER | CAPITAL_GEMM_B_UPPER));
+    Rfinal = Rf;
+  }
+  const int zd = g.y > g.x ? 1 : 0;  // local diagonal is below the global diagonal on those ranks
+  if (rstruct == CAPITAL_UPPERTRI_PACKED) CAP_TRY(pack_upper(ctx, st, nl, Rfinal, ld, dR, zd));
+  else CAP_TRY(triu_copy(ctx, st, nl, Rfinal, ld, dR, nl, zd));
+  CAP_TRY(copy_block(ctx, st, ml, nl, q.Q, q.ldq, dQ, ml));
+  CAP_TRY(cap_stage_out_end(ctx, Q_local, (size_t)ml * nl, dQ));
+  CAP_TRY(cap_stage_out_end(ctx, R_local, r_count, dR));
+  CAP_CUDA(cudaEventRecord(ctx->ev_stop, st));
+  return cap_check_info(ctx);
+}
+capital_status_t cacqr3d_residual(capital_ctx* ctx, const double* A_local, int64_t m, int64_t n, const double* Q_local,
+                                  capital_structure_t rstruct, const double* R_local, double* residual, double* orthogonality) {
+  const capital_grid_t& g = ctx->grid;
+  cudaStream_t st = ctx->stream;
+  Dist D{ctx, st, g};
+  Qr3 q{};
+  capital_cholinv_args_t dummy{1, 1, 0, 'U'};
+  CAP_TRY(qr3_setup(ctx, D, q, m, n, &dummy));
+  const int64_t ml = q.ml, nl = q.nl, ld = q.ldn;
+  const size_t r_count = rstruct == CAPITAL_UPPERTRI_PACKED ? (size_t)nl * (nl + 1) / 2 : (size_t)nl * nl;
+  const double *dA, *dQ, *dRin;
+  CAP_TRY(cap_stage_in(ctx, A_local, (size_t)ml * nl, "A_in", &dA));
+  CAP_TRY(cap_stage_in(ctx, Q_local, (size_t)ml * nl, "Q_in", &dQ));
+  CAP_TRY(cap_stage_in(ctx, R_local, r_count, "R_in", &dRin));
+  double* Rr = D.R;
+  if (rstruct == CAPITAL_UPPERTRI_PACKED) CAP_TRY(unpack_upper(ctx, st, nl, dRin, Rr, ld));
+  else CAP_TRY(triu_copy(ctx, st, nl, dRin, nl, Rr, ld, 0));
+  if (g.y > g.x) CAP_TRY(triu_copy(ctx, st, nl, Rr, ld, Rr, ld, 1));  // util::remove_triangle (validate.hpp:42)
+  CAP_CUDA(cudaMemsetAsync(ctx->d_scalars, 0, 3 * sizeof(double), st));
+  // residual: (Q R)^T - A^T = R^T Q^T - A^T
+  CAP_TRY(copy_block(ctx, st, ml, nl, dQ, ml, q.Q, q.ldq));
+  CAP_TRY(transpose_dist(D, ml, nl, q.Q, q.ldq, q.T1, ld));   // Q^T
+  CAP_TRY(copy_block(ctx, st, ml, nl, dA, ml, q.Q, q.ldq));
+  CAP_TRY(transpose_dist(D, ml, nl, q.Q, q.ldq, q.T2, ld));   // A^T
+  CAP_TRY(sumsq_block(ctx, st, nl, ml, q.T2, ld, 0, 0, 0, 1, ctx->d_scalars + 1));
+  CAP_TRY(product(D, nl, ml, nl, 1.0, Rr, ld, q.T1, ld, -1.0, q.T2, ld, CAPITAL_GEMM_A_UPPER));
+  CAP_TRY(sumsq_block(ctx, st, nl, ml, q.T2, ld, 0, 0, 0, 1, ctx->d_scalars));
+  // orthogonality: Q^T Q - I
+  CAP_TRY(copy_block(ctx, st, ml, nl, dQ, ml, q.Q, q.ldq));
+  CAP_TRY(product(D, nl, nl, ml, 1.0, q.Q, q.ldq, q.Q, q.ldq, 0.0, D.W, ld, 0));
+  if (g.x == g.y) CAP_TRY(sub_identity_local(ctx, st, nl, D.W, ld));
+  CAP_TRY(sumsq_block(ctx, st, nl, nl, D.W, ld, 0, 0, 0, 1, ctx->d_scalars + 2));
+  CAP_TRY(allreduce_scalars(ctx, ctx->d_scalars, 3));  // every layer holds a replica: all three sums carry the same factor c
+  double h[3];
+  CAP_CUDA(cudaMemcpyAsync(h, ctx->d_scalars, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CAP_CUDA(cudaStreamSynchronize(st));
+  *residual = sqrt(h[0]) / sqrt(h[1]);
+  *orthogonality = sqrt(h[2] / g.c) / sqrt((double)n * (double)n);
+  return CAPITAL_OK;
+}
+inline bool use_3d(const capital_grid_t& g) {
+  if (g.c != g.d) return false;
+  if (g.c > 1) return true;
+  const char* e = getenv("CAPITAL_FORCE_QR3D");  // 1x1x1: the reference takes the 1D path (cacqr.hpp:229); tests may force the 3D code
+  return e && atoi(e) != 0;
+}
+}  // namespace
+
 capital_status_t dist_cacqr_factor(capital_ctx* ctx, const double* A_local, int64_t m, int64_t n, int num_iter,
                                    const capital_cholinv_args_t* ci_args, capital_structure_t rstruct, double* Q_local, double* R_local) {
   (void)ci_args;
   const capital_grid_t& g = ctx->grid;
   CAP_TRY(need_comm(ctx));
+  if (use_3d(g)) return cacqr3d_factor(ctx, A_local, m, n, num_iter, ci_args, rstruct, Q_local, R_local);
   if (g.c != 1) {
-    ctx->set_error("cacqr: only the 1D grid (c == 1, cacqr.hpp:229) is implemented; 3D / tunable grids are a later row of the scope table");
+    ctx->set_error("cacqr: 1D (c == 1, cacqr.hpp:229) and 3D (c == d, :232) grids are implemented; the tunable c < d grid (:234-246) is not");
     return CAPITAL_ERR_UNSUPPORTED;
   }
   const int64_t lr = ceil_div(m, g.d);
@@ -696,6 +842,7 @@ capital_status_t dist_cacqr_residual(capital_ctx* ctx, const double* A_local, in
                                      capital_structure_t rstruct, const double* R_local, double* residual, double* orthogonality) {
   const capital_grid_t& g = ctx->grid;
   CAP_TRY(need_comm(ctx));
+  if (use_3d(g)) return cacqr3d_residual(ctx, A_local, m, n, Q_local, rstruct, R_local, residual, orthogonality);
   if (g.c != 1) return CAPITAL_ERR_UNSUPPORTED;
   const int64_t lr = ceil_div(m, g.d);
   cudaStream_t st = ctx->stream;

@@ -92,6 +92,19 @@ def main():
         es = np.abs(C.view2d().cpu().numpy() - ref).max()
         ok &= es < 1e-11
         msgs.append(f"summa gemm {c}x{d}x{d}: err={es:.1e}")
+    if world == 8:
+        # --- 3D CA-CholeskyQR2 (c = d = 2) against the reference's dump ---
+        meta, z = load("cacqr_p8_3d_m256_n64")
+        m, n = meta["m"], meta["n"]
+        t3 = cb.topo.rect(8, rank, 2)
+        A = cb.matrix(n, m, 2, 2).distribute_random(t3, rank // 2)
+        ok &= np.array_equal(A.data.cpu().numpy(), z[f"A_{rank}"])
+        qa = cb.cacqr.info(2, cb.cholinv.info(1, 1, -1, "U"))
+        cb.cacqr.factor(A, qa, t3)
+        eq = np.abs(qa.Q.cpu().numpy() - z[f"Q_{rank}"]).max()
+        res, orth = cb.cacqr.validate(A, qa, t3)
+        ok &= eq < 1e-12 and res < 1e-14 and orth < 1e-15
+        msgs.append(f"cacqr 3D golden: dQ={eq:.1e} res={res:.1e} orth={orth:.1e}")
     # --- 1D CholeskyQR2 on all ranks ---
     qt = cb.topo.rect(world, rank, 1)
     if world == 8:

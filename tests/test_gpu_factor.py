@@ -143,3 +143,21 @@ def test_summa_gemm_entry_point(topo, m, n, k):
     ref = 0.5 * (A.view2d().t() @ B.view2d()) - 2.0 * C.view2d()
     cb.summa.invoke(A, B, C, topo, alpha=0.5, beta=-2.0)
     assert (C.view2d() - ref).abs().max().item() < 1e-12
+
+
+@pytest.mark.parametrize("m,n,it", [(2048, 128, 2), (4096, 320, 2), (1024, 64, 1)])
+def test_cacqr_3d_code_path_on_degenerate_grid(m, n, it, monkeypatch):
+    """qr::cacqr::invoke_3d (cacqr.hpp:195-215) -- the SUMMA-based Gram / cholinv / trmm composition -- forced onto the 1x1x1 grid
+    (where the reference itself would take the 1D path) and compared with the 1D oracle: the factors are unique."""
+    monkeypatch.setenv("CAPITAL_FORCE_QR3D", "1")
+    topo = cb.topo.rect(1, 0, 1)
+    A = cb.matrix(n, m, 1, 1).distribute_random(topo, 11)
+    args = cb.cacqr.info(it, cb.cholinv.info(1, 1, -1, "U"))
+    cb.cacqr.factor(A, args, topo)
+    a = co.random_local(m, n, 1, 1, 0, 0, 11)
+    qs, r = co.cacqr_1d([a], it)
+    Q, R = cb.cacqr.construct_Q(args).cpu().numpy(), cb.cacqr.construct_R(args).cpu().numpy()
+    assert np.abs(R - r).max() < 1e-11 * np.abs(r).max()
+    assert np.abs(Q - qs[0]).max() < 1e-11
+    res, orth = cb.cacqr.validate(A, args, topo)
+    assert res < 1e-13 and orth < (1e-14 if it == 2 else 1e-12)
