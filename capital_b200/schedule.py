@@ -33,3 +33,29 @@ def summa_plan(c: int, d: int, rank: int) -> dict:
     plan["send_x_to"] = [r for r in plan["send_x_to"] if r != rank]
     plan["send_y_to"] = [r for r in plan["send_y_to"] if r != rank]
     return plan
+
+
+def product_slices(c: int, d: int, rank: int, k_local: int) -> list:
+    """Generalised schedule of dist.cu::product() for grids with c | d or d | c (the reference has c == d only).
+    The contraction index splits into d owner classes (k mod d = kb); layer z takes the classes kb = z (mod c) when c <= d,
+    and when c > d (2x1x1) the single class is cut into c/d row chunks of the local window.  Returns, for this rank, a list of
+    dicts {kb, rows=(r0, r1), src_x, src_y, send_x_to, send_y_to}; partial products are then summed over the depth group."""
+    assert c % d == 0 or d % c == 0
+    x, y, z = coords(c, d, rank)
+    nslices = max(c, d)
+    nchunk = c // d if c > d else 1
+    out = []
+    for sl in range(z, nslices, c):
+        kb, chunk = sl % d, sl // d
+        r0, r1 = 0, k_local
+        if nchunk > 1:
+            r0 = (k_local * chunk // nchunk) & ~1
+            r1 = k_local if chunk + 1 == nchunk else (k_local * (chunk + 1) // nchunk) & ~1
+        src = y == kb
+        out.append({
+            "kb": kb, "rows": (r0, r1),
+            "src_x": rank_of(c, d, y, kb, z), "src_y": rank_of(c, d, x, kb, z),
+            "send_x_to": [r for r in (rank_of(c, d, t, x, z) for t in range(d)) if r != rank] if src else [],
+            "send_y_to": [r for r in (rank_of(c, d, x, t, z) for t in range(d)) if r != rank] if src else [],
+        })
+    return out

@@ -63,3 +63,18 @@ def test_create_fails_loudly_without_device():
     g = cb.topo.square(1, 0, 1).grid
     with pytest.raises(_lib.CapitalError):
         _lib.Context(g, 0)
+
+
+def test_plain_c_caller_compiles_and_links():
+    """examples/cholinv_driver.c is the reference's bench main re-written against the C ABI in plain C: it must compile with gcc
+    (no CUDA headers) and link against the shared library; without a GPU it must fail loudly, not fall back."""
+    import subprocess, tempfile
+    exe = os.path.join(tempfile.mkdtemp(), "cholinv_driver")
+    libdir = os.path.join(ROOT, "capital_b200")
+    r = subprocess.run(["gcc", "-O2", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "cholinv_driver.c"),
+                        "-L" + libdir, "-lcapital_b200", "-Wl,-rpath," + libdir, "-lm", "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    import torch
+    if not torch.cuda.is_available():
+        run = subprocess.run([exe, "128", "1", "1", "1", "-1", "0", "0", "1"], capture_output=True, text=True)
+        assert run.returncode == 1 and "no sm_100 device" in run.stderr

@@ -62,6 +62,39 @@ def _summa_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _general_worker(rank, world, port, q, c, d):
+    """dist.cu::product() on the library's own non-cubic grids (2x1x1: k range split over the layers; 1x2x2: two SUMMA steps)."""
+    from capital_b200 import schedule as sch
+    from oracle import capital_oracle as co
+    _init(rank, world, port)
+    x, y, z = sch.coords(c, d, rank)
+    K, M, N = 16, 8, 12
+    rng = np.random.default_rng(1)
+    Xg, Yg = rng.standard_normal((K, M)), rng.standard_normal((K, N))
+    Xl, Yl = co.cyclic_local(Xg, d, d, x, y), co.cyclic_local(Yg, d, d, x, y)
+    P = np.zeros((M // d, N // d))
+    for sl in sch.product_slices(c, d, rank, K // d):
+        r0, r1 = sl["rows"]
+        xs, ys = np.ascontiguousarray(Xl[r0:r1]), np.ascontiguousarray(Yl[r0:r1])
+        reqs = [dist.isend(torch.from_numpy(xs), dst, tag=10 + sl["kb"]) for dst in sl["send_x_to"]]
+        reqs += [dist.isend(torch.from_numpy(ys), dst, tag=20 + sl["kb"]) for dst in sl["send_y_to"]]
+        xu, yu = torch.from_numpy(xs.copy()), torch.from_numpy(ys.copy())
+        if sl["src_x"] != rank:
+            dist.recv(xu, sl["src_x"], tag=10 + sl["kb"])
+        if sl["src_y"] != rank:
+            dist.recv(yu, sl["src_y"], tag=20 + sl["kb"])
+        for r in reqs:
+            r.wait()
+        P += xu.numpy().T @ yu.numpy()
+    allP = [torch.zeros(P.shape, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(allP, torch.from_numpy(P))
+    C = sum(allP[sch.rank_of(c, d, x, y, zz)].numpy() for zz in range(c))  # depth all-reduce
+    ok = np.allclose(C, co.cyclic_local(Xg.T @ Yg, d, d, x, y), atol=1e-12)
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def _qr_worker(rank, world, port, q):
     from oracle import capital_oracle as co
     _init(rank, world, port)
@@ -80,10 +113,10 @@ def _qr_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def _spawn(fn, world, port):
+def _spawn(fn, world, port, *extra):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=fn, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=fn, args=(r, world, port, q) + extra) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in range(world)]
@@ -94,6 +127,14 @@ def _spawn(fn, world, port):
 
 def test_summa_rank_arithmetic_on_2x2x2_gloo():
     _spawn(_summa_worker, 8, 29611)
+
+
+def test_product_on_2x1x1_world_size_2_gloo():
+    _spawn(_general_worker, 2, 29613, 2, 1)
+
+
+def test_product_on_1x2x2_world_size_4_gloo():
+    _spawn(_general_worker, 4, 29614, 1, 2)
 
 
 def test_cacqr_1d_gram_allreduce_world_size_2_gloo():

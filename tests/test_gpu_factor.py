@@ -161,3 +161,17 @@ def test_cacqr_3d_code_path_on_degenerate_grid(m, n, it, monkeypatch):
     assert np.abs(Q - qs[0]).max() < 1e-11
     res, orth = cb.cacqr.validate(A, args, topo)
     assert res < 1e-13 and orth < (1e-14 if it == 2 else 1e-12)
+
+
+def test_plain_c_caller_runs():
+    """the plain-C driver (reference bench protocol, host buffers) factors and validates on the GPU"""
+    import subprocess, tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(tempfile.mkdtemp(), "cholinv_driver")
+    libdir = os.path.join(root, "capital_b200")
+    subprocess.run(["gcc", "-O2", "-I" + os.path.join(root, "include"), os.path.join(root, "examples", "cholinv_driver.c"), "-L" + libdir,
+                    "-lcapital_b200", "-Wl,-rpath," + libdir, "-lm", "-o", exe], check=True)
+    r = subprocess.run([exe, "2048", "1", "0", "1", "-2", "0", "0", "2"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = r.stdout.strip().splitlines()
+    assert sum(l.startswith("total time - ") for l in lines) == 2 and float(lines[-1]) < 1e-14
