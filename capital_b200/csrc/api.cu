@@ -325,8 +325,16 @@ capital_status_t capital_cholinv_factor_f64(capital_ctx* ctx, const double* A_lo
   CAP_TRY(cap_stage_out_begin(ctx, R_local, out_count, "R_out", &dR));
   CAP_TRY(cap_stage_out_begin(ctx, Rinv_local, out_count, "Rinv_out", &dRinv));
   CAP_CUDA(cudaMemsetAsync(ctx->d_info, 0, sizeof(int), st));
-  CAP_CUDA(cudaMemsetAsync(Ri, 0, (size_t)ld * L * 8, st));
-  CAP_CUDA(cudaMemsetAsync(RiT, 0, (size_t)ld * L * 8, st));
+  if (ostruct == CAPITAL_RECT) {
+    CAP_CUDA(cudaMemsetAsync(Ri, 0, (size_t)ld * L * 8, st));  // rect outputs expose everything
+  } else {
+    CAP_TRY(zero_band(ctx, st, L, Ri, ld));
+    if (args->complete_inv == 0) {  // the skipped top-level block of Rinv (cholinv.hpp:147) must read as zeros in the packed output
+      const int64_t s1 = L >> args->split;
+      if (s1 > 0 && s1 < L) CAP_TRY(zero_block(ctx, st, s1, L - s1, Ri + s1 * ld, ld));
+    }
+  }
+  CAP_TRY(zero_band(ctx, st, L, RiT, ld));
   if (ostruct == CAPITAL_RECT) CAP_CUDA(cudaMemsetAsync(Rm, 0, (size_t)ld * L * 8, st));
 
   // Host-pointer callers: A streams in by column chunks on a copy stream while the recursion already works on the leading

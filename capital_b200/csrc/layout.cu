@@ -147,6 +147,15 @@ __global__ void sub_identity_kernel(long long n, double* __restrict__ a, long lo
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) a[i * ld + i] -= 1.0;
 }
 
+// zero the band |row - col| <= hw of an n x n matrix
+__global__ void zero_band_kernel(long long n, long long hw, double* __restrict__ a, long long ld) {
+  const long long w = 2 * hw + 1, total = n * w;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long c = idx / w, r = c - hw + (idx - c * w);
+    if (r >= 0 && r < n) a[c * ld + r] = 0.0;
+  }
+}
+
 inline int grid_for(const capital_ctx* ctx, long long total, int threads) {
   long long b = (total + threads - 1) / threads;
   const long long cap = (long long)ctx->num_sms * 8;
@@ -235,6 +244,21 @@ capital_status_t sumsq_block(capital_ctx* ctx, cudaStream_t st, int64_t rows, in
 }
 capital_status_t sub_identity_local(capital_ctx* ctx, cudaStream_t st, int64_t n, double* a, int64_t ld) {
   sub_identity_kernel<<<grid_for(ctx, n, 256), 256, 0, st>>>(n, a, ld);
+  LAUNCH_CHECK();
+  return CAPITAL_OK;
+}
+
+// The triangular products read whole diagonal GEMM tiles (<= 128 wide) of Rinv / Rinv^T, including entries on the other side of
+// the diagonal that no kernel writes; everything farther than one tile from the diagonal is either written before it is read
+// or never read.  Zeroing the band |row - col| <= 256 therefore replaces a memset of the whole n x n buffer.
+capital_status_t zero_band(capital_ctx* ctx, cudaStream_t st, int64_t n, double* a, int64_t ld) {
+  if (n <= 0) return CAPITAL_OK;
+  const int64_t hw = 256;
+  if (n <= 4 * hw) {
+    CAP_CUDA(cudaMemsetAsync(a, 0, (size_t)ld * n * 8, st));
+    return CAPITAL_OK;
+  }
+  zero_band_kernel<<<grid_for(ctx, n * (2 * hw + 1), 256), 256, 0, st>>>(n, hw, a, ld);
   LAUNCH_CHECK();
   return CAPITAL_OK;
 }
