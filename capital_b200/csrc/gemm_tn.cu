@@ -78,10 +78,17 @@ __global__ void __launch_bounds__(((BM / WM) * (BN / WN) + 4) * 32, MINB)
   constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
 
   const int flags = p.flags;
-  // Longest-tile-first: with a triangular operand the k extent grows with the tile index, so launch order is reversed
-  // to put the long tiles in the first wave and the short ones in the tail.
-  const int tm = (flags & CAPITAL_GEMM_A_UPPER) ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
-  const int tn = (flags & CAPITAL_GEMM_B_UPPER) ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+  // Longest-tile-first over the WHOLE grid: with a triangular operand the k extent depends on one tile coordinate only, so the
+  // linear CTA id is mapped to tiles in order of decreasing k extent (row-major over the other coordinate).  The first wave then
+  // holds the longest tiles and second residents / the tail get the short ones (a per-column reversal alone interleaves long and
+  // short tiles and lets two long tiles share an SM).
+  const int lin = (int)(blockIdx.x + gridDim.x * blockIdx.y);
+  int tm, tn;
+  if (flags & CAPITAL_GEMM_A_UPPER) { tm = (int)gridDim.x - 1 - lin / (int)gridDim.y; tn = lin % (int)gridDim.y; }
+  else if (flags & CAPITAL_GEMM_B_UPPER) { tn = (int)gridDim.y - 1 - lin / (int)gridDim.x; tm = lin % (int)gridDim.x; }
+  else if (flags & CAPITAL_GEMM_A_LOWER) { tm = lin / (int)gridDim.y; tn = lin % (int)gridDim.y; }
+  else if (flags & CAPITAL_GEMM_B_LOWER) { tn = lin / (int)gridDim.x; tm = lin % (int)gridDim.x; }
+  else { tm = (int)blockIdx.x; tn = (int)blockIdx.y; }
   const int m0 = tm * BM, n0 = tn * BN;
   const int n0g = n0 + p.noff;  // column position used by the structure tests
   if ((flags & CAPITAL_GEMM_C_UPPER) && m0 > n0g + BN - 1) return;  // tile strictly below the diagonal
