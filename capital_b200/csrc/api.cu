@@ -107,18 +107,27 @@ capital_status_t hostio_left_done(void* user, cudaStream_t st, int64_t col_end, 
   // miss the off-diagonal inverse blocks of the right-spine ancestors, computed after their right children)
   const bool rinv_too = depth == 0 || (depth == 1 && io->rinv_streams && io->rinv_cols_out == c0);
   const size_t off = (size_t)c0 * (c0 + 1) / 2, cnt = (size_t)col_end * (col_end + 1) / 2 - off;
-  CAP_TRY(pack_upper(ctx, st, io->L, io->Rm, io->ld, io->dR, 0, c0, col_end));
-  if (rinv_too) CAP_TRY(pack_upper(ctx, st, io->L, io->Ri, io->ld, io->dRinv, 0, c0, col_end));
+  // packing is HBM-bound filler work: it goes to the low-priority stream (joined before cholinv_local returns), not to the chain
+  // (host callers keep it on the chain: the D2H of the range should start right away, not behind queued deferred work)
+  cudaStream_t ps = (ctx->side && !ctx->no_overlap && !io->hR && !io->hRinv) ? ctx->side : st;
   cudaEvent_t e;
+  if (ps != st) {
+    CAP_TRY(io_event(ctx, &e));
+    CAP_CUDA(cudaEventRecord(e, st));
+    CAP_CUDA(cudaStreamWaitEvent(ps, e, 0));
+  }
+  CAP_TRY(pack_upper(ctx, ps, io->L, io->Rm, io->ld, io->dR, 0, c0, col_end));
+  if (rinv_too) CAP_TRY(pack_upper(ctx, ps, io->L, io->Ri, io->ld, io->dRinv, 0, c0, col_end));
+  io->cols_out = col_end;
+  if (rinv_too) io->rinv_cols_out = col_end;
+  if (!io->hR && !io->hRinv) return CAPITAL_OK;  // device outputs: nothing to copy out
   CAP_TRY(io_event(ctx, &e));
-  CAP_CUDA(cudaEventRecord(e, st));
+  CAP_CUDA(cudaEventRecord(e, ps));
   CAP_CUDA(cudaStreamWaitEvent(ctx->copy_out, e, 0));
   if (io->hR) { CAP_CUDA(cudaMemcpyAsync(io->hR + off, io->dR + off, cnt * 8, cudaMemcpyDeviceToHost, ctx->copy_out)); ctx->counters.d2h_bytes += (int64_t)cnt * 8; }
   if (io->hRinv && rinv_too) { CAP_CUDA(cudaMemcpyAsync(io->hRinv + off, io->dRinv + off, cnt * 8, cudaMemcpyDeviceToHost, ctx->copy_out)); ctx->counters.d2h_bytes += (int64_t)cnt * 8; }
   CAP_TRY(io_event(ctx, &io->e_out));
   CAP_CUDA(cudaEventRecord(io->e_out, ctx->copy_out));
-  io->cols_out = col_end;
-  if (rinv_too) io->rinv_cols_out = col_end;
   return CAPITAL_OK;
 }
 }  // namespace
@@ -367,7 +376,7 @@ capital_status_t capital_cholinv_factor_f64(capital_ctx* ctx, const double* A_lo
   } else {
     CAP_TRY(copy_block(ctx, st, L, L, A_local, L, W, ld));  // serialize(A -> R), cholinv.hpp:13
   }
-  if (io.packed && (io.hR || io.hRinv)) hooks.left_done = hostio_left_done;
+  if (io.packed && L >= 2048) hooks.left_done = hostio_left_done;  // finished column ranges are packed (and copied out) early
   const int64_t bc = capital_cholinv_bc_dimension(L, g.c, g.d, args->bc_mult_dim);
   CAP_TRY(cholinv_local(ctx, st, L, W, ld, Rm, ld, Ri, ld, RiT, ld, args->complete_inv != 0, bc, (int)args->split, &hooks));
   if (ostruct == CAPITAL_UPPERTRI_PACKED) {
