@@ -31,8 +31,8 @@ __device__ __forceinline__ double fast_rsqrt(double d) {
   if (!(d > 1e-30 && d < 1e30)) return rsqrt(d);
   double y = (double)rsqrtf((float)d);
   const double h = 0.5 * d;
-  y = y * (1.5 - h * y * y);
-  y = y * (1.5 - h * y * y);
+  y = y * fma(-h, y * y, 1.5);  // three dependent FP64 ops per Newton step
+  y = y * fma(-h, y * y, 1.5);
   return y;
 }
 
@@ -251,11 +251,11 @@ __device__ __forceinline__ void static_for(F&& f) {
 }
 
 // c[i] = A(i, lane) (upper part meaningful) -> R written to sRb (element (i, j) at sRb[j * TLD + i]), x[i] = Rinv(i, lane).
-// ub: 128 doubles of shared scratch (the scaled pivot row is broadcast through it: one conflict-free store and
+// ub: 896 doubles of shared scratch (the scaled pivot row is broadcast through it: one conflict-free store and
 // pipelined broadcast loads per pivot instead of 2 x 31 dependent shuffles).  The next pivot's rsqrt is started as
 // soon as its diagonal entry is final, so it overlaps with the rest of the rank-1 update.
-__device__ __forceinline__ void warp_potrf_trtri_32(double (&c)[32], double (&x)[32], double* __restrict__ sRb, double* __restrict__ ub,
-                                                    int lane, int* info, int pivot_base, long long* dbg2) {
+__device__ __forceinline__ void warp_potrf_trtri_32(double (&c)[32], double* __restrict__ sRb, double* __restrict__ sXb, double* __restrict__ sXTb,
+                                                    double* __restrict__ ub, int lane, int* info, int pivot_base, long long* dbg2) {
   double myrs = 0.0;
   if (dbg2 && lane == 0) dbg2[0] = clock64();
   // Two pivots per step.  With a = A(k,k), l = A(k,k+1), b = A(k+1,k+1) the second pivot is det / a, det = a b - l^2, so
@@ -296,26 +296,69 @@ __device__ __forceinline__ void warp_potrf_trtri_32(double (&c)[32], double (&x)
   });
   if (dbg2 && lane == 0) dbg2[1] = clock64();
 #pragma unroll
-  for (int i = 0; i < 32; i++) {
-    sRb[lane * TLD + i] = c[i];  // c[i] == 0 below the diagonal by construction (u = 0 for lane < k)
-    x[i] = (i == lane) ? myrs : 0.0;
+  for (int i = 0; i < 32; i++) sRb[lane * TLD + i] = c[i];  // c[i] == 0 below the diagonal by construction (u = 0 for lane < k)
+  __syncwarp();
+  // ---- inverse.  Phase A: the two 16 x 16 diagonal blocks at once (half-warp g owns block g; lane = column), so the
+  // back-substitution chain is 15 steps instead of 31.  xl[r] = X(16 g + r, lane).
+  const int g16 = lane >> 4, jl = lane & 15, base = 16 * g16;
+  double xl[16];
+  static_for<0, 16>([&](auto rc_) { constexpr int r = decltype(rc_)::value; xl[r] = (r == jl) ? myrs : 0.0; });
+  static_for<0, 15>([&](auto sc) {
+    constexpr int il = 14 - decltype(sc)::value;
+    const double rsi = shfl_d(myrs, base + il);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    static_for<il + 1, 16>([&](auto tc) {  // xl[t] == 0 for t > jl
+      constexpr int t = decltype(tc)::value;
+      const double rit = sRb[(base + t) * TLD + base + il];
+      if constexpr ((t & 3) == 0) s0 = fma(rit, xl[t], s0);
+      else if constexpr ((t & 3) == 1) s1 = fma(rit, xl[t], s1);
+      else if constexpr ((t & 3) == 2) s2 = fma(rit, xl[t], s2);
+      else s3 = fma(rit, xl[t], s3);
+    });
+    if (jl > il) xl[il] = -rsi * ((s0 + s1) + (s2 + s3));
+  });
+  // publish the diagonal blocks: xs[lane * 16 + r] (scratch, for phase B) and the output tiles
+  double* xs = ub + 128;        // 32 x 16
+  double* ts = ub + 128 + 512;  // 16 x 16
+  static_for<0, 16>([&](auto rc_) {
+    constexpr int r = decltype(rc_)::value;
+    xs[lane * 16 + r] = xl[r];
+    sXb[lane * TLD + base + r] = xl[r];
+    sXTb[(base + r) * TLD + lane] = xl[r];
+  });
+  __syncwarp();
+  // Phase B: X12 = -X11 R12 X22 (16 x 16 blocks).  Lane (g, jl) owns column jl of the block and rows 8 g .. 8 g + 7.
+  {
+    double rc[16], tr[8];
+    static_for<0, 16>([&](auto tc) { constexpr int t = decltype(tc)::value; rc[t] = sRb[(16 + jl) * TLD + t]; });  // R(t, 16 + jl)
+    static_for<0, 8>([&](auto rr) {
+      constexpr int r = decltype(rr)::value;
+      const int i = 8 * g16 + r;
+      double s = 0.0;
+      static_for<0, 16>([&](auto tc) {  // X11(i, t) = xs[t * 16 + i], zero for t < i
+        constexpr int t = decltype(tc)::value;
+        s = fma(xs[t * 16 + i], rc[t], s);
+      });
+      tr[r] = s;
+      ts[jl * 16 + i] = s;  // T(i, jl)
+    });
+    __syncwarp();
+    double xc[16];
+    static_for<0, 16>([&](auto tc) { constexpr int t = decltype(tc)::value; xc[t] = xs[(16 + jl) * 16 + t]; });  // X22(t, jl), zero for t > jl
+    static_for<0, 8>([&](auto rr) {
+      constexpr int r = decltype(rr)::value;
+      const int i = 8 * g16 + r;
+      double s = 0.0;
+      static_for<0, 16>([&](auto tc) {
+        constexpr int t = decltype(tc)::value;
+        s = fma(ts[t * 16 + i], xc[t], s);
+      });
+      sXb[(16 + jl) * TLD + i] = -s;
+      sXTb[i * TLD + 16 + jl] = -s;
+    });
+    (void)tr;
   }
   __syncwarp();
-  // column `lane` of X = R^{-1}: X(i, j) = -rs_i * sum_{t = i+1..j} R(i, t) X(t, j);  R(i, t) read as a broadcast from sRb
-#pragma unroll
-  for (int i = 30; i >= 0; i--) {
-    const double rsi = shfl_d(myrs, i);
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-    for (int t = i + 1; t < 32; t++) {  // x[t] == 0 for t > lane
-      const double rit = sRb[t * TLD + i];
-      if ((t & 3) == 0) s0 = fma(rit, x[t], s0);
-      else if ((t & 3) == 1) s1 = fma(rit, x[t], s1);
-      else if ((t & 3) == 2) s2 = fma(rit, x[t], s2);
-      else s3 = fma(rit, x[t], s3);
-    }
-    if (lane > i) x[i] = -rsi * ((s0 + s1) + (s2 + s3));
-  }
   if (dbg2 && lane == 0) dbg2[2] = clock64();
 }
 
@@ -346,7 +389,7 @@ __device__ void leaf64_fast(double* __restrict__ sA, double* __restrict__ sR, do
     sR[cidx * TLD + r] = 0.0; sX[cidx * TLD + r] = 0.0; sXT[cidx * TLD + r] = 0.0;
   }
   __syncthreads();
-  double c[32], x[32];
+  double c[32];
 #pragma unroll 1
   for (int half = 0; half < 2; half++) {
     const int o = half * 32;
@@ -371,13 +414,9 @@ __device__ void leaf64_fast(double* __restrict__ sA, double* __restrict__ sR, do
     if (w == 0) {
 #pragma unroll
       for (int i = 0; i < 32; i++) c[i] = sA[(o + lane) * TLD + o + i];
-      warp_potrf_trtri_32(c, x, sR + o * TLD + o, ub, lane, info, pivot_base + o, (dbg2 && half == 0) ? dbg2 : nullptr);
+      warp_potrf_trtri_32(c, sR + o * TLD + o, sX + o * TLD + o, sXT + o * TLD + o, ub, lane, info, pivot_base + o,
+                          (dbg2 && half == 0) ? dbg2 : nullptr);
       if (dbg2 && half == 0 && lane == 0) dbg2[3] = clock64();
-#pragma unroll
-      for (int i = 0; i < 32; i++) {
-        sX[(o + lane) * TLD + o + i] = x[i];
-        sXT[(o + i) * TLD + o + lane] = x[i];
-      }
     }
     __syncthreads();
   }
@@ -593,7 +632,7 @@ capital_status_t leaf_cholinv(capital_ctx* ctx, cudaStream_t st, int nb, const d
 capital_status_t basecase_cholinv(capital_ctx* ctx, cudaStream_t st, int nb, double* W, int64_t ldw, double* R, int64_t ldr, double* Ri,
                                   int64_t ldri, double* RiT, int64_t ldrit) {
   if (nb % 64 != 0 || nb < 64 || nb > BASECASE_MAX || RiT == nullptr) return CAPITAL_ERR_INVALID;
-  constexpr int smem = (4 * TILE_DOUBLES + 128) * (int)sizeof(double);
+  constexpr int smem = (4 * TILE_DOUBLES + 128 + 512 + 256) * (int)sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
     CAP_CUDA(cudaFuncSetAttribute(basecase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
