@@ -144,6 +144,11 @@ struct Dist {
   // contiguous transfer buffers
   double *bufX, *bufY, *bufP, *bufS;  // fetched X, fetched Y, partial/all-reduced product, send staging (2 blocks)
   ncclComm_t world, depth, slice;
+  // host-pointer callers: finished column ranges are packed and copied out while the rest of the factorization runs
+  bool stream_out = false, rinv_streams = false;
+  double *dR = nullptr, *dRinv = nullptr, *hR = nullptr, *hRinv = nullptr;
+  int64_t cols_out = 0, rinv_cols_out = 0;
+  cudaEvent_t e_out = nullptr;
 };
 
 // pack a (rows x cols) window into a contiguous buffer with even leading dimension
@@ -380,8 +385,40 @@ capital_status_t base_case(Dist& D, int64_t o, int64_t s) {
   return CAPITAL_OK;
 }
 
+capital_status_t dist_io_event(capital_ctx* ctx, cudaEvent_t* e) {
+  if (ctx->io_used == ctx->io_pool.size()) {
+    cudaEvent_t ev;
+    CAP_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    ctx->io_pool.push_back(ev);
+  }
+  *e = ctx->io_pool[ctx->io_used++];
+  return CAPITAL_OK;
+}
+// local columns [cols_out, col_end) of R are final (of Rinv too left of the top split, and up to the next split when the top-level
+// inverse block is skipped): pack that contiguous range of the packed triangle and start its D2H on the copy-out stream
+capital_status_t dist_left_done(Dist& D, int64_t col_end, int depth) {
+  capital_ctx* ctx = D.ctx;
+  const int64_t c0 = D.cols_out;
+  if (col_end <= c0) return CAPITAL_OK;
+  const bool rinv_too = depth == 0 || (depth == 1 && D.rinv_streams && D.rinv_cols_out == c0);
+  const size_t off = (size_t)c0 * (c0 + 1) / 2, cnt = (size_t)col_end * (col_end + 1) / 2 - off;
+  CAP_TRY(pack_upper(ctx, D.st, D.L, D.R, D.ld, D.dR, 0, c0, col_end));
+  if (rinv_too) CAP_TRY(pack_upper(ctx, D.st, D.L, D.Ri, D.ld, D.dRinv, 0, c0, col_end));
+  D.cols_out = col_end;
+  if (rinv_too) D.rinv_cols_out = col_end;
+  cudaEvent_t e;
+  CAP_TRY(dist_io_event(ctx, &e));
+  CAP_CUDA(cudaEventRecord(e, D.st));
+  CAP_CUDA(cudaStreamWaitEvent(ctx->copy_out, e, 0));
+  if (D.hR) { CAP_CUDA(cudaMemcpyAsync(D.hR + off, D.dR + off, cnt * 8, cudaMemcpyDeviceToHost, ctx->copy_out)); ctx->counters.d2h_bytes += (int64_t)cnt * 8; }
+  if (D.hRinv && rinv_too) { CAP_CUDA(cudaMemcpyAsync(D.hRinv + off, D.dRinv + off, cnt * 8, cudaMemcpyDeviceToHost, ctx->copy_out)); ctx->counters.d2h_bytes += (int64_t)cnt * 8; }
+  CAP_TRY(dist_io_event(ctx, &D.e_out));
+  CAP_CUDA(cudaEventRecord(D.e_out, ctx->copy_out));
+  return CAPITAL_OK;
+}
+
 // cholinv::invoke (cholinv.hpp:87-165) on the local window [o, o+s)
-capital_status_t invoke(Dist& D, int64_t o, int64_t s, bool complete) {
+capital_status_t invoke(Dist& D, int64_t o, int64_t s, bool complete, int depth = 0) {
   capital_ctx* ctx = D.ctx;
   const int64_t s1 = s >> D.split;
   if (s <= D.bc_local || s1 < D.split || s1 == 0) return base_case(D, o, s);
@@ -395,10 +432,11 @@ capital_status_t invoke(Dist& D, int64_t o, int64_t s, bool complete) {
   double* Ri22 = D.Ri + (o + s1) * ld + (o + s1);
   double* RiT11 = D.RiT + o * ld + o;
   double* RiT21 = D.RiT + o * ld + (o + s1);
-  CAP_TRY(invoke(D, o, s1, true));
+  CAP_TRY(invoke(D, o, s1, true, depth + 1));
+  if (D.stream_out && depth <= 3 && o + s == D.L) CAP_TRY(dist_left_done(D, o + s1, depth));  // right spine
   CAP_TRY(product(D, s1, s2, s1, 1.0, Ri11, ld, W12, ld, 0.0, R12, ld, CAPITAL_GEMM_A_UPPER));       // cholinv.hpp:116-122
   CAP_TRY(product(D, s2, s2, s1, -1.0, R12, ld, R12, ld, 1.0, W22, ld, CAPITAL_GEMM_C_UPPER));        // :131-134
-  CAP_TRY(invoke(D, o + s1, s2, true));
+  CAP_TRY(invoke(D, o + s1, s2, true, depth + 1));
   if (complete) {                                                                                       // :147-155
     CAP_TRY(product(D, s2, s1, s1, 1.0, R12, ld, RiT11, ld, 0.0, W21, ld, CAPITAL_GEMM_B_LOWER));
     CAP_TRY(product(D, s1, s2, s2, -1.0, W21, ld, Ri22, ld, 0.0, Ri12, ld, CAPITAL_GEMM_B_UPPER));
@@ -509,16 +547,33 @@ capital_status_t dist_cholinv_factor(capital_ctx* ctx, const double* A_local, in
       ctx->counters.h2d_bytes += rows * nc * 8;
     }
   }
+  D.dR = dR; D.dRinv = dRinv;
+  D.hR = dR != R_local ? R_local : nullptr;
+  D.hRinv = dRinv != Rinv_local ? Rinv_local : nullptr;
+  D.stream_out = ostruct == CAPITAL_UPPERTRI_PACKED && (D.hR || D.hRinv) && L >= 2048;
+  D.rinv_streams = args->complete_inv == 0;
+  ctx->io_used = 0;
   CAP_TRY(invoke(D, 0, L, args->complete_inv != 0));
   if (ostruct == CAPITAL_UPPERTRI_PACKED) {
-    CAP_TRY(pack_upper(ctx, st, L, D.R, ld, dR, 0));
-    CAP_TRY(pack_upper(ctx, st, L, D.Ri, ld, dRinv, 0));
+    {
+      const int64_t c0 = D.cols_out;
+      const size_t off = (size_t)c0 * (c0 + 1) / 2, cnt = out_count - off;
+      CAP_TRY(pack_upper(ctx, st, L, D.R, ld, dR, 0, c0, L));
+      if (D.hR) { CAP_CUDA(cudaMemcpyAsync(D.hR + off, dR + off, cnt * 8, cudaMemcpyDeviceToHost, st)); ctx->counters.d2h_bytes += (int64_t)cnt * 8; }
+    }
+    {
+      const int64_t c0 = D.rinv_cols_out;
+      const size_t off = (size_t)c0 * (c0 + 1) / 2, cnt = out_count - off;
+      CAP_TRY(pack_upper(ctx, st, L, D.Ri, ld, dRinv, 0, c0, L));
+      if (D.hRinv) { CAP_CUDA(cudaMemcpyAsync(D.hRinv + off, dRinv + off, cnt * 8, cudaMemcpyDeviceToHost, st)); ctx->counters.d2h_bytes += (int64_t)cnt * 8; }
+    }
+    if (D.e_out) CAP_CUDA(cudaStreamWaitEvent(st, D.e_out, 0));
   } else {
     CAP_TRY(triu_copy(ctx, st, L, D.R, ld, dR, L, 0));
     CAP_TRY(triu_copy(ctx, st, L, D.Ri, ld, dRinv, L, 0));
+    CAP_TRY(cap_stage_out_end(ctx, R_local, out_count, dR));
+    CAP_TRY(cap_stage_out_end(ctx, Rinv_local, out_count, dRinv));
   }
-  CAP_TRY(cap_stage_out_end(ctx, R_local, out_count, dR));
-  CAP_TRY(cap_stage_out_end(ctx, Rinv_local, out_count, dRinv));
   CAP_CUDA(cudaEventRecord(ctx->ev_stop, st));
   return cap_check_info(ctx);
 }

@@ -78,6 +78,21 @@ def main():
             ok &= er < 2e-13 and ei < 2e-13 and res < 1e-12
             msgs.append(f"grid {c}x{d}x{d} n={n} ci={ci}: dR={er:.1e} dRinv={ei:.1e} res={res:.1e}")
     if world in (2, 4, 8):
+        # --- host-pointer path of the distributed factor (upper-triangle H2D, streamed D2H) == resident path, bit for bit ---
+        c = {2: 2, 4: 1, 8: 2}[world]
+        topo = cb.topo.square(world, rank, c)
+        d = topo.d
+        for n, ci in ((4096 * d, 0), (2048 * d, 1)):
+            A = cb.matrix(n, n, d, d).distribute_symmetric(topo)
+            dev = cb.cholinv.info(ci, 1, -3, "U")
+            cb.cholinv.factor(A, dev, topo)
+            hostA = cb.matrix(n, n, d, d, data=A.data.cpu().pin_memory())
+            hst = cb.cholinv.info(ci, 1, -3, "U")
+            cb.cholinv.factor(hostA, hst, topo)
+            same = torch.equal(hst.R, dev.R.cpu()) and torch.equal(hst.Rinv, dev.Rinv.cpu())
+            ok &= same and not hst.R.is_cuda
+            msgs.append(f"host path n={n} ci={ci}: identical={same}")
+    if world in (2, 4, 8):
         # --- SUMMA GEMM entry point (T*N) on the same grid, against the global product ---
         c = {2: 2, 4: 1, 8: 2}[world]
         topo = cb.topo.square(world, rank, c)
