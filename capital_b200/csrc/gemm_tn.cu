@@ -110,7 +110,10 @@ __global__ void __launch_bounds__(((BM / WM) * (BN / WN) + 4) * 32, MINB)
   }
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment for the 128B swizzle, computed as an OFFSET into the shared array so that the pointer keeps its
+  // shared address space (fragment loads then compile to LDS.128 instead of generic LD.E.128)
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_u32 + 1023u) & ~1023u) - raw_u32);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t full0 = smem_base + STAGES * STAGE_BYTES;
   const uint32_t empty0 = full0 + STAGES * 8;
