@@ -78,3 +78,17 @@ def test_plain_c_caller_compiles_and_links():
     if not torch.cuda.is_available():
         run = subprocess.run([exe, "128", "1", "1", "1", "-1", "0", "0", "1"], capture_output=True, text=True)
         assert run.returncode == 1 and "no sm_100 device" in run.stderr
+
+
+def test_product_path_never_touches_the_oracle():
+    """oracle/ is test infrastructure: the package (product path) must not import, link or execute anything under it, and the
+    library must not silently fall back to a CPU path (capital_create refuses anything but an sm_100 device)."""
+    import glob
+    pkg = os.path.join(ROOT, "capital_b200")
+    for path in glob.glob(os.path.join(pkg, "*.py")) + glob.glob(os.path.join(pkg, "csrc", "*.cu*")):
+        if os.path.basename(path) == "build.py":
+            continue
+        src = open(path).read()
+        assert "oracle" not in src.replace("the oracle", ""), path
+    api = open(os.path.join(pkg, "csrc", "api.cu")).read()
+    assert "prop.major != 10" in api and "no fallback" in api
