@@ -226,9 +226,9 @@ def ours(args):
             "residual": residual,
             "roofline": {"bound": "tensor", "achieved": ach, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
                          "frac": (ach / DMMA_PEAK_TFLOPS) if ach else None,
-                         # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the two launches captured with
-                         # `ncu --set full` (profiles/r01b_gemm_tn_ncu_full.md: 2.45 GB and 0.99 GB against 0.67 / 0.40 GB algorithmic)
-                         "traffic": 1.72e9 if world == 1 else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the three launches captured with
+                         # `ncu --set full` (profiles/r01e_gemm_tn_ncu_full.md: 0.06 / 0.68 / 8.53 GB for the 2048 / 4096 / 8192 levels)
+                         "traffic": 3.09e9 if world == 1 else None,
                          "kernel": "gemm_tn_kernel<128,128,64,32,5> (DMMA.8x8x4 + TMA)", "launches": s_launches,
                          "kernel_share_of_step": s_ms / s_ms_step if s_ms_step else None,
                          "measured_in": "one extra step after the timed region with the deferred stream disabled (single-stream step "
