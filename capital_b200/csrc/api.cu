@@ -130,6 +130,39 @@ capital_status_t hostio_left_done(void* user, cudaStream_t st, int64_t col_end, 
   CAP_CUDA(cudaEventRecord(io->e_out, ctx->copy_out));
   return CAPITAL_OK;
 }
+int64_t hostio_cols_waited(void* user) { return ((HostIO*)user)->waited; }
+// pack columns [done, col_end) of R (or Rinv) on the chain and queue their D2H on the copy-out stream (host outputs only)
+capital_status_t hostio_emit(HostIO* io, cudaStream_t st, bool r_part, int64_t col_end) {
+  capital_ctx* ctx = io->ctx;
+  int64_t& done = r_part ? io->cols_out : io->rinv_cols_out;
+  const int64_t c0 = done;
+  if (col_end <= c0) return CAPITAL_OK;
+  const double* src = r_part ? io->Rm : io->Ri;
+  double* dev = r_part ? io->dR : io->dRinv;
+  double* host = r_part ? io->hR : io->hRinv;
+  const size_t off = (size_t)c0 * (c0 + 1) / 2, cnt = (size_t)col_end * (col_end + 1) / 2 - off;
+  CAP_TRY(pack_upper(ctx, st, io->L, src, io->ld, dev, 0, c0, col_end));
+  done = col_end;
+  if (!host) return CAPITAL_OK;
+  cudaEvent_t e;
+  CAP_TRY(io_event(ctx, &e));
+  CAP_CUDA(cudaEventRecord(e, st));
+  CAP_CUDA(cudaStreamWaitEvent(ctx->copy_out, e, 0));
+  CAP_CUDA(cudaMemcpyAsync(host + off, dev + off, cnt * 8, cudaMemcpyDeviceToHost, ctx->copy_out));
+  ctx->counters.d2h_bytes += (int64_t)cnt * 8;
+  CAP_TRY(io_event(ctx, &io->e_out));
+  CAP_CUDA(cudaEventRecord(io->e_out, ctx->copy_out));
+  return CAPITAL_OK;
+}
+// the top-level right child is done: R is final everywhere (and so is Rinv when the top-level inverse block is skipped); its last
+// columns leave while the top-level inverse block is still being computed
+capital_status_t hostio_right_done(void* user, cudaStream_t st) {
+  HostIO* io = (HostIO*)user;
+  CAP_TRY(hostio_emit(io, st, true, io->L));
+  if (io->rinv_streams) CAP_TRY(hostio_emit(io, st, false, io->L));
+  return CAPITAL_OK;
+}
+capital_status_t hostio_inv_cols(void* user, cudaStream_t st, int64_t col_end) { return hostio_emit((HostIO*)user, st, false, col_end); }
 }  // namespace
 
 extern "C" {
@@ -377,6 +410,11 @@ capital_status_t capital_cholinv_factor_f64(capital_ctx* ctx, const double* A_lo
     CAP_TRY(copy_block(ctx, st, L, L, A_local, L, W, ld));  // serialize(A -> R), cholinv.hpp:13
   }
   if (io.packed && L >= 2048) hooks.left_done = hostio_left_done;  // finished column ranges are packed (and copied out) early
+  if (hooks.need_cols) hooks.cols_waited = hostio_cols_waited;
+  if (hooks.left_done && (io.hR || io.hRinv)) {  // host outputs: the tail of R and the top-level inverse block stream out too
+    hooks.right_done = hostio_right_done;
+    if (io.hRinv) hooks.inv_cols = hostio_inv_cols;
+  }
   const int64_t bc = capital_cholinv_bc_dimension(L, g.c, g.d, args->bc_mult_dim);
   CAP_TRY(cholinv_local(ctx, st, L, W, ld, Rm, ld, Ri, ld, RiT, ld, args->complete_inv != 0, bc, (int)args->split, &hooks));
   if (ostruct == CAPITAL_UPPERTRI_PACKED) {
@@ -384,13 +422,13 @@ capital_status_t capital_cholinv_factor_f64(capital_ctx* ctx, const double* A_lo
       const int64_t c0 = io.cols_out;
       const size_t off = (size_t)c0 * (c0 + 1) / 2, cnt = out_count - off;
       CAP_TRY(pack_upper(ctx, st, L, Rm, ld, dR, 0, c0, L));
-      if (io.hR) { CAP_CUDA(cudaMemcpyAsync(io.hR + off, dR + off, cnt * 8, cudaMemcpyDeviceToHost, st)); ctx->counters.d2h_bytes += (int64_t)cnt * 8; }
+      if (io.hR && cnt) { CAP_CUDA(cudaMemcpyAsync(io.hR + off, dR + off, cnt * 8, cudaMemcpyDeviceToHost, st)); ctx->counters.d2h_bytes += (int64_t)cnt * 8; }
     }
     {
       const int64_t c0 = io.rinv_cols_out;
       const size_t off = (size_t)c0 * (c0 + 1) / 2, cnt = out_count - off;
       CAP_TRY(pack_upper(ctx, st, L, Ri, ld, dRinv, 0, c0, L));
-      if (io.hRinv) { CAP_CUDA(cudaMemcpyAsync(io.hRinv + off, dRinv + off, cnt * 8, cudaMemcpyDeviceToHost, st)); ctx->counters.d2h_bytes += (int64_t)cnt * 8; }
+      if (io.hRinv && cnt) { CAP_CUDA(cudaMemcpyAsync(io.hRinv + off, dRinv + off, cnt * 8, cudaMemcpyDeviceToHost, st)); ctx->counters.d2h_bytes += (int64_t)cnt * 8; }
     }
     if (io.e_out) CAP_CUDA(cudaStreamWaitEvent(st, io.e_out, 0));  // the early D2H of the left half
   } else {

@@ -27,6 +27,8 @@ int64_t split_point(int64_t n) {
   return s1;
 }
 
+constexpr int64_t IN_CHUNK = 2048;  // columns per launch of an R12 product issued while A is still arriving from the host
+
 struct Rec {
   capital_ctx* ctx;
   cudaStream_t M, S;  // critical chain / deferred work
@@ -90,10 +92,23 @@ capital_status_t rec(Rec& r, int64_t o, int64_t n, bool complete, cudaEvent_t pe
   CAP_TRY(rec(r, o, s1, true, nullptr, depth + 1));
   // right spine only (o + n == total size): everything left of column o + s1 is final for R
   if (depth <= 3 && o + n == r.total && r.hooks && r.hooks->left_done) CAP_TRY(r.hooks->left_done(r.hooks->user, r.M, o + s1, depth));
-  if (r.hooks && r.hooks->need_cols) CAP_TRY(r.hooks->need_cols(r.hooks->user, r.M, o + n));
-  if (pending) CAP_CUDA(cudaStreamWaitEvent(r.M, pending, 0));  // the parent's deferred update covers W12 and W22
   // "trsm" via the inverse (cholinv.hpp:116-122): R12 = Rinv11^T A12
-  CAP_TRY(gemm_tn(ctx, r.M, s1, s2, s1, 1.0, Ri, ldri, W12, ldw, 0.0, R12, ldr, CAPITAL_GEMM_A_UPPER));
+  const bool inflight = r.hooks && r.hooks->need_cols && r.hooks->cols_waited && r.hooks->cols_waited(r.hooks->user) < o + n;
+  if (inflight && s2 >= 2 * IN_CHUNK) {
+    // A is still arriving from the host (left spine of the recursion): issue the product by column chunks, each waiting for its own
+    // columns only, so that the tensor pipe starts on A12 while the copy engine is still delivering its right part
+    if (pending) CAP_CUDA(cudaStreamWaitEvent(r.M, pending, 0));
+    for (int64_t c0 = 0; c0 < s2;) {
+      const int64_t nc = (s2 - c0 < IN_CHUNK + IN_CHUNK / 2) ? s2 - c0 : IN_CHUNK;
+      CAP_TRY(r.hooks->need_cols(r.hooks->user, r.M, o + s1 + c0 + nc));
+      CAP_TRY(gemm_tn(ctx, r.M, s1, nc, s1, 1.0, Ri, ldri, W12 + c0 * ldw, ldw, 0.0, R12 + c0 * ldr, ldr, CAPITAL_GEMM_A_UPPER));
+      c0 += nc;
+    }
+  } else {
+    if (r.hooks && r.hooks->need_cols) CAP_TRY(r.hooks->need_cols(r.hooks->user, r.M, o + n));
+    if (pending) CAP_CUDA(cudaStreamWaitEvent(r.M, pending, 0));  // the parent's deferred update covers W12 and W22
+    CAP_TRY(gemm_tn(ctx, r.M, s1, s2, s1, 1.0, Ri, ldri, W12, ldw, 0.0, R12, ldr, CAPITAL_GEMM_A_UPPER));
+  }
   cudaEvent_t e_r12 = nullptr, e_tt = nullptr, e_far = nullptr;
   const bool use_side = r.S != nullptr && s1 >= r.ctx->side_min;
   if (use_side) {
@@ -125,10 +140,28 @@ capital_status_t rec(Rec& r, int64_t o, int64_t n, bool complete, cudaEvent_t pe
     }
   }
   CAP_TRY(rec(r, o + s1, s2, true, e_far, depth + 1));
+  if (depth == 0 && r.hooks && r.hooks->right_done) CAP_TRY(r.hooks->right_done(r.hooks->user, r.M));
   if (complete) {
     if (e_tt) CAP_CUDA(cudaStreamWaitEvent(r.M, e_tt, 0));
     //   Rinv12 = -(T^T)^T Rinv22  (B = Ri22, upper triangular)   (cholinv.hpp:152-155)
-    CAP_TRY(gemm_tn(ctx, r.M, s1, s2, s2, -1.0, W21, ldw, Ri22, ldri, 0.0, Ri12, ldri, CAPITAL_GEMM_B_UPPER));
+    const int64_t ct = s2 / 128;  // whole 128-column tiles of the block
+    if (depth == 0 && r.hooks && r.hooks->inv_cols && ct >= 32) {
+      // last product of the factorization, and the host is waiting for its result: four column chunks (the k extent grows with the
+      // column, so the leading half is cheap), each handed to the copy-out stream as soon as it is done; only the D2H of the last,
+      // narrow chunk stays exposed.  Chunk edges are multiples of the 128-column tile: every tile computes exactly what it computes
+      // in the single launch.
+      const int64_t e3 = ct - ct * 3 / 32, e2 = e3 - ct * 5 / 32, e1 = e2 - ct / 4;
+      const int64_t edge[5] = {0, e1 * 128, e2 * 128, e3 * 128, s2};
+      for (int i = 0; i < 4; i++) {
+        const int64_t c0 = edge[i], c1 = edge[i + 1];
+        if (c1 <= c0) continue;
+        CAP_TRY(gemm_tn_off(ctx, r.M, s1, c1 - c0, c1, -1.0, W21, ldw, Ri22 + c0 * ldri, ldri, 0.0, Ri12 + c0 * ldri, ldri,
+                            CAPITAL_GEMM_B_UPPER, 0, (int)c0));
+        CAP_TRY(r.hooks->inv_cols(r.hooks->user, r.M, o + s1 + c1));
+      }
+    } else {
+      CAP_TRY(gemm_tn(ctx, r.M, s1, s2, s2, -1.0, W21, ldw, Ri22, ldri, 0.0, Ri12, ldri, CAPITAL_GEMM_B_UPPER));
+    }
     CAP_TRY(transpose_block(ctx, r.M, s1, s2, Ri12, ldri, RiT21, ldrit, 1.0));
   }
   return CAPITAL_OK;

@@ -147,6 +147,13 @@ struct CholinvHooks {
   void* user;
   capital_status_t (*need_cols)(void* user, cudaStream_t st, int64_t col_end);
   capital_status_t (*left_done)(void* user, cudaStream_t st, int64_t col_end, int depth);
+  // optional (host-pointer callers).  `cols_waited`: how many leading columns the chain already waited for -- while it is short of a
+  // node's extent, the node's R12 product is issued in column chunks, each behind the arrival of its own columns only.
+  // `right_done`: the top-level right child has returned, all of R is final.  `inv_cols`: the top-level inverse block is issued in
+  // column chunks; columns [0, col_end) of Rinv are final.
+  int64_t (*cols_waited)(void* user);
+  capital_status_t (*right_done)(void* user, cudaStream_t st);
+  capital_status_t (*inv_cols)(void* user, cudaStream_t st, int64_t col_end);
 };
 capital_status_t cholinv_local(capital_ctx* ctx, cudaStream_t st, int64_t n, double* W, int64_t ldw, double* R, int64_t ldr,
                                double* Ri, int64_t ldri, double* RiT, int64_t ldrit, bool complete_top, int64_t bc, int split,

@@ -330,6 +330,7 @@ capital_status_t gemm_tn_off(capital_ctx* ctx, cudaStream_t st, int64_t m, int64
   const bool atri = flags & (CAPITAL_GEMM_A_UPPER | CAPITAL_GEMM_A_LOWER), btri = flags & (CAPITAL_GEMM_B_UPPER | CAPITAL_GEMM_B_LOWER);
   if (atri && btri) f = 2.0 * (double)m * (double)n * (double)k / 3.0;
   else if (atri) f = (double)n * (double)m * (double)(m + 1);
+  else if (btri && (flags & CAPITAL_GEMM_B_UPPER) && noff > 0 && koff == 0 && k >= noff + n) f = (double)m * (double)n * (double)(2 * (int64_t)noff + n + 1);
   else if (btri) f = (double)m * (double)n * (double)(n + 1);
   else if (flags & CAPITAL_GEMM_C_UPPER) f = (double)k * (double)m * (double)(m + 1);
   ctx->counters.gemm_flops += f;

@@ -74,6 +74,25 @@ def test_cholinv_host_pointers_and_reuse(topo):
     assert np.abs(co.unpack_upper(args.Rinv.numpy(), n) - ri_o).max() < 1e-13
 
 
+@pytest.mark.parametrize("n,ci", [(8192, 1), (8192, 0), (9088, 1)])
+def test_cholinv_streamed_host_path_equals_resident_path(topo, n, ci):
+    """host buffers at a size where A12 is multiplied while it is still arriving and the top-level inverse block leaves in column
+    chunks: every tile computes what it computes in the resident schedule, so the outputs are identical bit for bit."""
+    A = cb.matrix(n, n, 1, 1).distribute_symmetric(topo)
+    dev = cb.cholinv.info(ci, 1, -4, "U")
+    cb.cholinv.factor(A, dev, topo)
+    hostA = cb.matrix(n, n, 1, 1, data=A.data.cpu().pin_memory())
+    hst = cb.cholinv.info(ci, 1, -4, "U")
+    ctx = topo.context()
+    for _ in range(2):
+        ctx.reset_counters()
+        cb.cholinv.factor(hostA, hst, topo)
+        assert ctx.counters().d2h_bytes == 2 * (n * (n + 1) // 2) * 8
+    assert not hst.R.is_cuda and not hst.Rinv.is_cuda
+    assert torch.equal(hst.R, dev.R.cpu()) and torch.equal(hst.Rinv, dev.Rinv.cpu())
+    assert cb.cholinv.residual(A, dev, topo) <= 1e-12
+
+
 def test_cholinv_rejects_non_spd(topo):
     n = 256
     A = cb.matrix(n, n, 1, 1).distribute_symmetric(topo)
