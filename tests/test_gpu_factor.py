@@ -74,7 +74,7 @@ def test_cholinv_host_pointers_and_reuse(topo):
     assert np.abs(co.unpack_upper(args.Rinv.numpy(), n) - ri_o).max() < 1e-13
 
 
-@pytest.mark.parametrize("n,ci", [(8192, 1), (8192, 0), (9088, 1)])
+@pytest.mark.parametrize("n,ci", [(8192, 1), (8192, 0), (9088, 1), (16384, 0)])
 def test_cholinv_streamed_host_path_equals_resident_path(topo, n, ci):
     """host buffers at a size where A12 is multiplied while it is still arriving and the top-level inverse block leaves in column
     chunks: every tile computes what it computes in the resident schedule, so the outputs are identical bit for bit."""
