@@ -419,7 +419,6 @@ capital_status_t dist_left_done(Dist& D, int64_t col_end, int depth) {
 
 // cholinv::invoke (cholinv.hpp:87-165) on the local window [o, o+s)
 capital_status_t invoke(Dist& D, int64_t o, int64_t s, bool complete, int depth = 0) {
-  capital_ctx* ctx = D.ctx;
   const int64_t s1 = s >> D.split;
   if (s <= D.bc_local || s1 < D.split || s1 == 0) return base_case(D, o, s);
   const int64_t s2 = s - s1, ld = D.ld;
