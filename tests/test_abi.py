@@ -1,6 +1,5 @@
 """CPU-side checks of the boundary: the shared library loads, exports every symbol the header declares, and the
 pure host helpers (grids, base-case size) agree with the oracle restatement.  No compute calls (no GPU here)."""
-import ctypes as C
 import os, re
 import pytest
 import capital_b200 as cb

@@ -2,7 +2,6 @@
 2x2x2 grid (8 processes) and the 1D CholeskyQR2 reduction on 2 processes, against the global-view oracle."""
 import os, sys
 import numpy as np
-import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp

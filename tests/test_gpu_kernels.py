@@ -1,6 +1,5 @@
 """GPU parity of the leaf kernels through the C ABI: DMMA GEMM (every structure flag, ragged and unaligned
 windows), fused potrf+trtri, and the generators (bit-exact against the oracle restatement)."""
-import ctypes as C
 import numpy as np
 import pytest
 import torch

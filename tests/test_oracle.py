@@ -1,6 +1,6 @@
 """Pin the CPU restatement (oracle/capital_oracle.py) against the reference's own outputs
 (tests/golden/*.npz, dumped by the reference compiled in oracle/_ref) and against LAPACK."""
-import glob, json, os
+import json, os
 import numpy as np
 import pytest
 import scipy.linalg as sla
