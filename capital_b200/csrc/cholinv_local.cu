@@ -74,11 +74,17 @@ capital_status_t rec(Rec& r, int64_t o, int64_t n, bool complete, cudaEvent_t pe
   double* RiT = r.RiT + o * r.ldrit + o;
   const int64_t ldw = r.ldw, ldr = r.ldr, ldri = r.ldri, ldrit = r.ldrit;
   const int64_t s1 = choose_split(r, o, n, complete);
+  const bool blocks = r.hooks && r.hooks->block_done;  // experimental block-wise output (common.cuh)
   if (s1 == 0) {
     if (r.hooks && r.hooks->need_cols) CAP_TRY(r.hooks->need_cols(r.hooks->user, r.M, o + n));
     if (pending) CAP_CUDA(cudaStreamWaitEvent(r.M, pending, 0));
-    if (n <= LEAF_MAX) return leaf_cholinv(ctx, r.M, (int)n, W, ldw, R, ldr, Ri, ldri, RiT, ldrit);
-    return basecase_cholinv(ctx, r.M, (int)n, W, ldw, R, ldr, Ri, ldri, RiT, ldrit);
+    if (n <= LEAF_MAX) CAP_TRY(leaf_cholinv(ctx, r.M, (int)n, W, ldw, R, ldr, Ri, ldri, RiT, ldrit));
+    else CAP_TRY(basecase_cholinv(ctx, r.M, (int)n, W, ldw, R, ldr, Ri, ldri, RiT, ldrit));
+    if (blocks && depth <= ctx->zc_depth) {  // a leaf above the emission depth: its triangle is a unit of the tiling
+      CAP_TRY(r.hooks->block_done(r.hooks->user, r.M, 0, o, o + n, o, o + n));
+      CAP_TRY(r.hooks->block_done(r.hooks->user, r.M, 1, o, o + n, o, o + n));
+    }
+    return CAPITAL_OK;
   }
   const int64_t s2 = n - s1;
   double* W12 = W + s1 * ldw;
@@ -89,6 +95,8 @@ capital_status_t rec(Rec& r, int64_t o, int64_t n, bool complete, cudaEvent_t pe
   double* Ri22 = Ri + s1 * ldri + s1;
   double* RiT21 = RiT + s1;
 
+  // the skipped inverse block (complete_inv == 0) is part of the output all the same: zeros, written by the caller before the recursion
+  if (blocks && depth < ctx->zc_depth && !complete) CAP_TRY(r.hooks->block_done(r.hooks->user, r.M, 1, o, o + s1, o + s1, o + n));
   CAP_TRY(rec(r, o, s1, true, nullptr, depth + 1));
   // right spine only (o + n == total size): everything left of column o + s1 is final for R
   if (depth <= 3 && o + n == r.total && r.hooks && r.hooks->left_done) CAP_TRY(r.hooks->left_done(r.hooks->user, r.M, o + s1, depth));
@@ -109,6 +117,7 @@ capital_status_t rec(Rec& r, int64_t o, int64_t n, bool complete, cudaEvent_t pe
     if (pending) CAP_CUDA(cudaStreamWaitEvent(r.M, pending, 0));  // the parent's deferred update covers W12 and W22
     CAP_TRY(gemm_tn(ctx, r.M, s1, s2, s1, 1.0, Ri, ldri, W12, ldw, 0.0, R12, ldr, CAPITAL_GEMM_A_UPPER));
   }
+  if (blocks && depth < ctx->zc_depth) CAP_TRY(r.hooks->block_done(r.hooks->user, r.M, 0, o, o + s1, o + s1, o + n));  // R12 is final
   cudaEvent_t e_r12 = nullptr, e_tt = nullptr, e_far = nullptr;
   const bool use_side = r.S != nullptr && s1 >= r.ctx->side_min;
   if (use_side) {
@@ -162,7 +171,12 @@ capital_status_t rec(Rec& r, int64_t o, int64_t n, bool complete, cudaEvent_t pe
     } else {
       CAP_TRY(gemm_tn(ctx, r.M, s1, s2, s2, -1.0, W21, ldw, Ri22, ldri, 0.0, Ri12, ldri, CAPITAL_GEMM_B_UPPER));
     }
+    if (blocks && depth < ctx->zc_depth) CAP_TRY(r.hooks->block_done(r.hooks->user, r.M, 1, o, o + s1, o + s1, o + n));
     CAP_TRY(transpose_block(ctx, r.M, s1, s2, Ri12, ldri, RiT21, ldrit, 1.0));
+  }
+  if (blocks && depth == ctx->zc_depth) {  // diagonal triangle of a node at the emission depth
+    CAP_TRY(r.hooks->block_done(r.hooks->user, r.M, 0, o, o + n, o, o + n));
+    CAP_TRY(r.hooks->block_done(r.hooks->user, r.M, 1, o, o + n, o, o + n));
   }
   return CAPITAL_OK;
 }

@@ -44,6 +44,10 @@ struct capital_ctx {
   cudaStream_t side = nullptr;     // low-priority stream: deferred ("far") trailing updates, T^T products
   cudaStream_t hi = nullptr;       // high-priority stream: the critical chain of the recursion
   cudaStream_t copy_in = nullptr, copy_out = nullptr;  // H2D / D2H streams of the host-pointer path
+  // EXPERIMENTAL, off by default [env CAPITAL_ZC_OUT=1]: host outputs leave block by block through a kernel that stores straight
+  // into the pinned packed arrays (partial columns can leave as soon as they are final; see profiles/r01f_e2e_notes.md)
+  cudaStream_t zc_out = nullptr;
+  int zc_mode = 0, zc_ctas = 8, zc_depth = 3;  // [env CAPITAL_ZC_CTAS, CAPITAL_ZC_DEPTH]
   std::vector<cudaEvent_t> dep_pool;  // dependency events (timing disabled), recycled per factor call
   size_t dep_used = 0;
   std::vector<cudaEvent_t> io_pool;   // events of the host-pointer streaming path
@@ -116,6 +120,8 @@ capital_status_t zero_block(capital_ctx* ctx, cudaStream_t st, int64_t rows, int
 capital_status_t zero_band(capital_ctx* ctx, cudaStream_t st, int64_t n, double* a, int64_t ld);
 capital_status_t pack_upper(capital_ctx* ctx, cudaStream_t st, int64_t n, const double* src, int64_t lds, double* packed,
                             int zero_diag, int64_t col_begin = 0, int64_t col_end = -1);
+capital_status_t emit_block_packed(capital_ctx* ctx, cudaStream_t st, const double* src, int64_t lds, double* packed, int64_t r0, int64_t r1,
+                                   int64_t c0, int64_t c1, int ctas);
 capital_status_t unpack_upper(capital_ctx* ctx, cudaStream_t st, int64_t n, const double* packed, double* dst, int64_t ldd);
 capital_status_t triu_copy(capital_ctx* ctx, cudaStream_t st, int64_t n, const double* src, int64_t lds, double* dst,
                            int64_t ldd, int zero_diag);
@@ -154,6 +160,10 @@ struct CholinvHooks {
   int64_t (*cols_waited)(void* user);
   capital_status_t (*right_done)(void* user, cudaStream_t st);
   capital_status_t (*inv_cols)(void* user, cudaStream_t st, int64_t col_end);
+  // optional, exclusive with left_done / right_done / inv_cols: rows [r0, r1) x columns [c0, c1) (clipped to the upper triangle) of
+  // R (which = 0) or Rinv (which = 1) are final on stream `st`.  Fired for the off-diagonal block of every node above depth
+  // ctx->zc_depth and for the diagonal triangle of the nodes at that depth (or leaves above it): together they tile the triangle.
+  capital_status_t (*block_done)(void* user, cudaStream_t st, int which, int64_t r0, int64_t r1, int64_t c0, int64_t c1);
 };
 capital_status_t cholinv_local(capital_ctx* ctx, cudaStream_t st, int64_t n, double* W, int64_t ldw, double* R, int64_t ldr,
                                double* Ri, int64_t ldri, double* RiT, int64_t ldrit, bool complete_top, int64_t bc, int split,
