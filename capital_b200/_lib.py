@@ -13,8 +13,8 @@ GEMM_A_UPPER, GEMM_A_LOWER, GEMM_B_UPPER, GEMM_B_LOWER, GEMM_C_UPPER = 1, 2, 4, 
 
 EXPORTS = [  # every symbol include/capital_b200.h declares
     "capital_grid_square", "capital_grid_rect", "capital_cholinv_bc_dimension", "capital_create",
-    "capital_comm_unique_id", "capital_comm_init", "capital_destroy", "capital_last_error", "capital_get_counters",
-    "capital_reset_counters", "capital_synchronize", "capital_last_factor_ms", "capital_profile_begin", "capital_profile_end", "capital_set_overlap", "capital_distribute_symmetric_f64",
+    "capital_comm_unique_id", "capital_comm_init", "capital_comm_init_host", "capital_dist_trace_cholinv", "capital_destroy", "capital_last_error", "capital_get_counters",
+    "capital_reset_counters", "capital_synchronize", "capital_set_stream", "capital_release_workspace", "capital_last_factor_ms", "capital_profile_begin", "capital_profile_end", "capital_set_overlap", "capital_distribute_symmetric_f64",
     "capital_distribute_random_f64", "capital_cholinv_factor_f64", "capital_cholinv_residual_f64",
     "capital_cacqr_factor_f64", "capital_cacqr_residual_f64", "capital_summa_gemm_tn_f64", "capital_blas_gemm_tn_f64",
     "capital_lapack_potrf_trtri_f64",
@@ -32,6 +32,9 @@ class CholinvArgs(C.Structure):
 class Counters(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("gemm_launches", C.c_int64), ("leaf_launches", C.c_int64),
                 ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("gemm_flops", C.c_double)]
+
+
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64)
 
 
 class CapitalError(RuntimeError):
@@ -58,6 +61,8 @@ def lib() -> C.CDLL:
     L.capital_create.argtypes = [C.POINTER(vp), C.POINTER(Grid), ci, vp]
     L.capital_comm_unique_id.argtypes = [vp]
     L.capital_comm_init.argtypes = [vp, vp]
+    L.capital_comm_init_host.argtypes = [vp, ALLGATHER_FN, vp]
+    L.capital_dist_trace_cholinv.argtypes = [C.POINTER(Grid), i64, C.POINTER(CholinvArgs), C.POINTER(i64), i64, C.POINTER(i64)]
     L.capital_destroy.argtypes = [vp]
     L.capital_destroy.restype = None
     L.capital_last_error.argtypes = [vp]
@@ -65,6 +70,8 @@ def lib() -> C.CDLL:
     L.capital_get_counters.argtypes = [vp, C.POINTER(Counters)]
     L.capital_reset_counters.argtypes = [vp]
     L.capital_synchronize.argtypes = [vp]
+    L.capital_set_stream.argtypes = [vp, vp]
+    L.capital_release_workspace.argtypes = [vp]
     L.capital_last_factor_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.capital_profile_begin.argtypes = [vp]
     L.capital_set_overlap.argtypes = [vp, ci]
@@ -114,6 +121,13 @@ class Context:
 
     def synchronize(self):
         self.check(lib().capital_synchronize(self._h))
+
+    def set_stream(self, stream: int):
+        self.check(lib().capital_set_stream(self._h, C.c_void_p(stream)))
+
+    def release_workspace(self):
+        """policy::cholinv::FlushIntermediates: free every work buffer (re-allocated by the next call)."""
+        self.check(lib().capital_release_workspace(self._h))
 
     def last_factor_ms(self) -> float:
         ms = C.c_float()

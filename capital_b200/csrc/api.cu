@@ -54,6 +54,10 @@ capital_status_t cap_check_info(capital_ctx* ctx) {
   int info = 0;
   CAP_CUDA(cudaMemcpyAsync(&info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CAP_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (info < 0) {
+    ctx->set_error("a wait on a peer GPU timed out (a rank of the grid died, or the ranks did not make the same sequence of calls)");
+    return CAPITAL_ERR_COMM;
+  }
   if (info != 0) {
     ctx->set_error("matrix is not positive definite: non-positive pivot " + std::to_string(info) + " in a base-case block");
     return CAPITAL_ERR_NOT_SPD;
@@ -256,6 +260,7 @@ capital_status_t capital_create(capital_ctx** out, const capital_grid_t* grid, i
   ok = ok && cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn != nullptr;
   if (!ok) { capital_destroy(ctx); return CAPITAL_ERR_CUDA; }
   ctx->encode = (cuTensorMapEncodeTiled_fn)fn;
+  if (gemm_tn_init(ctx) != CAPITAL_OK || leaf_init(ctx) != CAPITAL_OK) { capital_destroy(ctx); return CAPITAL_ERR_CUDA; }
   if (const char* e = getenv("CAPITAL_KCHUNK")) ctx->kchunk = atoll(e);
   if (const char* e = getenv("CAPITAL_FAR_MIN")) ctx->far_min = atoll(e);
   if (const char* e = getenv("CAPITAL_SIDE_MIN")) ctx->side_min = atoll(e);
@@ -306,6 +311,28 @@ capital_status_t capital_reset_counters(capital_ctx* ctx) {
 capital_status_t capital_synchronize(capital_ctx* ctx) {
   if (!ctx) return CAPITAL_ERR_INVALID;
   CAP_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CAPITAL_OK;
+}
+capital_status_t capital_set_stream(capital_ctx* ctx, void* stream) {
+  if (!ctx || !stream) return CAPITAL_ERR_INVALID;
+  CAP_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t ns = (cudaStream_t)stream;
+  if (ns == ctx->stream) return CAPITAL_OK;
+  // order the new stream after the work already enqueued on the old one (workspaces are shared between calls)
+  CAP_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+  CAP_CUDA(cudaStreamWaitEvent(ns, ctx->ev_fork, 0));
+  if (ctx->own_stream) { CAP_CUDA(cudaStreamSynchronize(ctx->stream)); CAP_CUDA(cudaStreamDestroy(ctx->stream)); ctx->own_stream = false; }
+  ctx->stream = ns;
+  return CAPITAL_OK;
+}
+capital_status_t capital_release_workspace(capital_ctx* ctx) {
+  if (!ctx) return CAPITAL_ERR_INVALID;
+  CAP_CUDA(cudaSetDevice(ctx->device));
+  CAP_CUDA(cudaDeviceSynchronize());  // side / copy streams may still reference the buffers
+  CAP_TRY(dist_release_peer_maps(ctx));
+  for (auto& kv : ctx->pool) if (kv.second.p) CAP_CUDA(cudaFree(kv.second.p));
+  ctx->pool.clear();
+  if (ctx->pinned) { CAP_CUDA(cudaFreeHost(ctx->pinned)); ctx->pinned = nullptr; ctx->pinned_bytes = 0; }
   return CAPITAL_OK;
 }
 capital_status_t capital_last_factor_ms(const capital_ctx* ctx_, float* ms) {
@@ -403,11 +430,14 @@ capital_status_t capital_cholinv_factor_f64(capital_ctx* ctx, const double* A_lo
     CAP_TRY(cap_stage_out_begin(ctx, Rinv_local, out_count, "Rinv_out", &dRinv));
   }
   CAP_CUDA(cudaMemsetAsync(ctx->d_info, 0, sizeof(int), st));
+  const int64_t bc = capital_cholinv_bc_dimension(L, g.c, g.d, args->bc_mult_dim);
   if (ostruct == CAPITAL_RECT) {
     CAP_CUDA(cudaMemsetAsync(Ri, 0, (size_t)ld * L * 8, st));  // rect outputs expose everything
   } else {
     CAP_TRY(zero_band(ctx, st, L, Ri, ld));
-    if (args->complete_inv == 0) {  // the skipped top-level block of Rinv (cholinv.hpp:147) must read as zeros in the packed output
+    // the skipped top-level block of Rinv (cholinv.hpp:147) must read as zeros in the packed output -- it only exists when the top
+    // node splits (same predicate as cholinv_local: a top-level base case returns the full inverse)
+    if (args->complete_inv == 0 && cholinv_node_splits(L, bc, (int)args->split)) {
       const int64_t s1 = L >> args->split;
       if (s1 > 0 && s1 < L) CAP_TRY(zero_block(ctx, st, s1, L - s1, Ri + s1 * ld, ld));
     }
@@ -421,7 +451,7 @@ capital_status_t capital_cholinv_factor_f64(capital_ctx* ctx, const double* A_lo
   io.ctx = ctx; io.L = L; io.ld = ld; io.Rm = Rm; io.Ri = Ri; io.dR = dR; io.dRinv = dRinv;
   io.hR = (dR != R_local) ? R_local : nullptr; io.hRinv = (dRinv != Rinv_local) ? Rinv_local : nullptr;
   io.packed = ostruct == CAPITAL_UPPERTRI_PACKED;
-  io.rinv_streams = args->complete_inv == 0;
+  io.rinv_streams = args->complete_inv == 0 && cholinv_node_splits(L, bc, (int)args->split);
   CholinvHooks hooks{&io, nullptr, nullptr};
   if (!cap_is_device_ptr(A_local)) {
     cudaEvent_t e0;
@@ -453,7 +483,6 @@ capital_status_t capital_cholinv_factor_f64(capital_ctx* ctx, const double* A_lo
     hooks.right_done = hostio_right_done;
     if (io.hRinv) hooks.inv_cols = hostio_inv_cols;
   }
-  const int64_t bc = capital_cholinv_bc_dimension(L, g.c, g.d, args->bc_mult_dim);
   CAP_TRY(cholinv_local(ctx, st, L, W, ld, Rm, ld, Ri, ld, RiT, ld, args->complete_inv != 0, bc, (int)args->split, &hooks));
   if (zR) {  // every block has been handed to the output stream inside the recursion
     cudaEvent_t e;

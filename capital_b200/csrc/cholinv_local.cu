@@ -48,7 +48,7 @@ struct Rec {
 // (cholinv.hpp:93-104) -- the recursion continues with 64-aligned halves down to the cluster / leaf kernels.
 // Returns 0 when the block is handled by a single kernel.
 int64_t choose_split(const Rec& r, int64_t o, int64_t n, bool complete) {
-  if (n > r.bc && (n >> r.split) >= r.split && (n >> r.split) > 0 && (n > LEAF_MAX || !complete)) return n >> r.split;
+  if (cholinv_node_splits(n, r.bc, r.split) && (n > LEAF_MAX || !complete)) return n >> r.split;
   if (n <= LEAF_MAX) return 0;
   if (n <= BASECASE_MAX && n % 64 == 0 && complete && r.base_aligned && (o & 1) == 0) return 0;
   return split_point(n);
@@ -185,10 +185,10 @@ capital_status_t rec(Rec& r, int64_t o, int64_t n, bool complete, cudaEvent_t pe
 
 capital_status_t cholinv_local(capital_ctx* ctx, cudaStream_t st, int64_t n, double* W, int64_t ldw, double* R, int64_t ldr, double* Ri,
                                int64_t ldri, double* RiT, int64_t ldrit, bool complete_top, int64_t bc, int split,
-                               const CholinvHooks* hooks) {
+                               const CholinvHooks* hooks, bool allow_side) {
   // `st` is the caller-visible stream; the recursion runs on the context's high-priority stream, fenced by events.
-  cudaStream_t M = ctx->hi ? ctx->hi : st;
-  cudaStream_t S = (ctx->hi && ctx->side && n >= 1024 && !ctx->no_overlap) ? ctx->side : nullptr;
+  cudaStream_t M = (ctx->hi && allow_side) ? ctx->hi : st;
+  cudaStream_t S = (allow_side && ctx->hi && ctx->side && n >= 1024 && !ctx->no_overlap) ? ctx->side : nullptr;
   ctx->dep_used = 0;
   cudaEvent_t e_in = nullptr, e_out = nullptr, e_s = nullptr;
   if (M != st) {
@@ -199,6 +199,9 @@ capital_status_t cholinv_local(capital_ctx* ctx, cudaStream_t st, int64_t n, dou
   }
   const bool aligned = ((((uintptr_t)W | (uintptr_t)R | (uintptr_t)Ri | (uintptr_t)RiT) & 15) == 0) && !((ldw | ldr | ldri | ldrit) & 1);
   Rec r{ctx, M, S, W, R, Ri, RiT, ldw, ldr, ldri, ldrit, bc, split, hooks, ctx->far_min, n, ctx->kchunk, aligned};
+  // a top-level node the reference treats as its base case (n <= bc, cholinv.hpp:93-104) gets the FULL inverse whatever complete_inv
+  // says; the skip of cholinv.hpp:147 only exists where the top node really splits at n >> split
+  if (!cholinv_node_splits(n, bc, split)) complete_top = true;
   CAP_TRY(rec(r, 0, n, complete_top, nullptr, 0));
   if (M != st) {
     if (S) {  // join the deferred stream (all its work has been consumed through events, this is just the fence)

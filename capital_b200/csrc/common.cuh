@@ -63,17 +63,12 @@ struct capital_ctx {
   // pinned staging for host-pointer callers
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
-  // NCCL (dlopen'ed; see comm.cu)
-  void* nccl_lib = nullptr;
-  void* comm_world = nullptr;
-  void* comm_row = nullptr;
-  void* comm_col = nullptr;
-  void* comm_depth = nullptr;
-  void* comm_slice = nullptr;
-  cudaStream_t comm_stream = nullptr;  // NCCL stream of the pipelined distributed products
-  std::vector<cudaEvent_t> comm_pool;
+  // multi-GPU: peer layer (peer.cuh) -- IPC-mapped arenas and flags; NCCL (dlopen'ed) only bootstraps the handle exchange
+  void* comm_world = nullptr;          // ncclComm_t, when capital_comm_init was used
+  void* peer = nullptr;                // Peer*
+  std::vector<cudaEvent_t> comm_pool;  // dependency events of the distributed schedules, recycled per call
   size_t comm_used = 0;
-  bool dist_pipeline = false;
+  std::string arena_signature;         // which layout the peer arena currently holds (a new layout starts from zeros)
 
   // per-launch timing of the dominant kernel (gemm_tn 128x128), off by default
   struct ProfRec { cudaEvent_t e0, e1; double flops; };
@@ -101,6 +96,42 @@ struct capital_ctx {
 };
 
 // ---- gemm_tn.cu -------------------------------------------------------------------------------
+capital_status_t gemm_tn_init(capital_ctx* ctx);  // per-device kernel attributes
+capital_status_t leaf_init(capital_ctx* ctx);
+
+// Multi-GPU form of the product (dist.cu).  (1) The contraction may run over several operand CLASSES -- the k-slices owned by
+// different process rows (summa.hpp:185-193), fetched into local mirrors -- inside one launch, accumulators staying in
+// registers.  (2) The depth reduction of the reference (MPI_Allreduce over the c layers, summa.hpp:236) is fused into the
+// epilogue over peer-mapped memory:
+//   mode 1 (k split over layers, c == d): every layer computes a partial of every tile; tile (tm, tn) is OWNED by layer
+//          (tm + tn) mod c.  Non-owners store their partial (in register-fragment order, 16-byte coalesced) straight into the
+//          owner's receive buffer over NVLink and raise a per-tile flag; the owner adds the partials to its accumulators,
+//          applies alpha / beta and stores the FINAL tile into the C replica of every layer.  Tiles are handed out by a ticket
+//          counter, all non-owned tiles before any owned one, so a waiting owner only ever waits for tiles that never wait.
+//   mode 2 (n split, d == 1): layer tn mod c computes tile column tn with the full k range and stores it to every replica.
+constexpr int GEMM_NCLS_MAX = 2;
+constexpr int GEMM_XPEERS_MAX = 3;
+struct GemmXDev {
+  int mode, c, z;
+  unsigned long long seq;                               // flag value of this product (monotonic over the context's lifetime)
+  unsigned int* ticket;                                 // zero on entry
+  double* Cpeer[GEMM_XPEERS_MAX];                       // C window inside the replica of the i-th OTHER layer
+  double* precv_local[GEMM_XPEERS_MAX];                 // my receive buffer for the i-th other layer's partials
+  double* precv_peer[GEMM_XPEERS_MAX];                  // the i-th other layer's receive buffer for MY partials
+  unsigned long long* tflag_local[GEMM_XPEERS_MAX];     // per-tile arrival flags, same indexing
+  unsigned long long* tflag_peer[GEMM_XPEERS_MAX];
+  int* err;                                             // set to -1 when a wait times out
+};
+struct GemmOperands {
+  int ncls = 1;
+  const double* A[GEMM_NCLS_MAX] = {nullptr, nullptr};
+  const double* B[GEMM_NCLS_MAX] = {nullptr, nullptr};
+  int64_t lda = 0, ldb = 0;
+};
+// bytes of receive buffer / number of tile flags a mode-1 product of this shape needs (per other layer)
+void gemm_tn_xsizes(const capital_ctx* ctx, int64_t m, int64_t n, size_t* precv_bytes, size_t* tiles);
+capital_status_t gemm_tn_x(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const GemmOperands& ops,
+                           double beta, double* C, int64_t ldc, int flags, int koff, int noff, const GemmXDev* x);
 capital_status_t gemm_tn(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
                          int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags);
 
@@ -165,9 +196,15 @@ struct CholinvHooks {
   // ctx->zc_depth and for the diagonal triangle of the nodes at that depth (or leaves above it): together they tile the triangle.
   capital_status_t (*block_done)(void* user, cudaStream_t st, int which, int64_t r0, int64_t r1, int64_t c0, int64_t c1);
 };
+// allow_side = false keeps everything on `st` (the distributed base case runs on the critical chain and must not queue behind
+// the deferred stream's GEMMs).
 capital_status_t cholinv_local(capital_ctx* ctx, cudaStream_t st, int64_t n, double* W, int64_t ldw, double* R, int64_t ldr,
                                double* Ri, int64_t ldri, double* RiT, int64_t ldrit, bool complete_top, int64_t bc, int split,
-                               const CholinvHooks* hooks = nullptr);
+                               const CholinvHooks* hooks = nullptr, bool allow_side = true);
 
 static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+// Does cholinv::invoke split a node of (global = local, single GPU) size n, or is it the reference's base case (potrf + trtri of the
+// whole block, cholinv.hpp:93)?  Decides whether complete_inv == 0 skips an inverse block at all: a top-level base case always
+// returns the full inverse.
+static inline bool cholinv_node_splits(int64_t n, int64_t bc, int split) { return n > bc && (n >> split) >= split && (n >> split) > 0; }
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

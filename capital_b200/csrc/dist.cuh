@@ -1,8 +1,9 @@
-// Multi-GPU side of the path: NCCL plumbing (dlopen'ed, one process per GPU) and the distributed schedules.
+// Multi-GPU side of the path: the distributed schedules over the peer layer (peer.cuh), one process per GPU.
 #pragma once
 #include "common.cuh"
 
 void dist_destroy(capital_ctx* ctx);
+capital_status_t dist_release_peer_maps(capital_ctx* ctx);  // collective: unmap / free the peer arena (capital_release_workspace)
 capital_status_t dist_cholinv_factor(capital_ctx* ctx, const double* A_local, int64_t n, const capital_cholinv_args_t* args,
                                      capital_structure_t ostruct, double* R_local, double* Rinv_local);
 capital_status_t dist_cholinv_residual(capital_ctx* ctx, const double* A_local, int64_t n, capital_structure_t structure,

@@ -26,9 +26,17 @@ struct GemmParams {
   int noff;    // column index of this window of B / C inside the full operand (column-chunked launches)
   int koff;    // row index of this window inside the full operand (k-chunked launches keep the triangular k ranges right)
   int ksplit;  // gridDim.z chunks of the k range; > 1 => epilogue accumulates with atomics (C pre-initialised, beta ignored)
+  int ncls;    // operand classes: the contraction runs over ncls (A_i, B_i) pairs with identical shapes (SUMMA k-slices, summa.hpp:185-193)
+  int gm, gn;  // tile grid
   double alpha, beta;
   double* C;
   long long ldc;
+  GemmXDev x;  // depth exchange fused into the epilogue (XMODE != 0)
+};
+
+struct GemmMaps {
+  CUtensorMap a[GEMM_NCLS_MAX];
+  CUtensorMap b[GEMM_NCLS_MAX];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -64,31 +72,74 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// barrier over the consumer warps only (the producer warpgroup has left the kernel by then)
+__device__ __forceinline__ void consumer_bar(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+
 constexpr int BK = 16;  // doubles per k tile = one 128-byte swizzle row
 
 // Warp roles: NCW consumer warps (whole warpgroups) + one producer warpgroup of which a single lane drives TMA.
 // Registers are allocated per warpgroup on sm_100, so a 9th warp would be charged as four anyway; with RC > 0 the
 // producer group hands its registers to the consumers (setmaxnreg), which is what lets a 64x32 warp tile
 // (128 accumulator registers) live without spills.
-template <int BM, int BN, int WM, int WN, int STAGES, int MINB, int RC, int RP>
+// XMODE: 0 = plain product; 1 / 2 = depth exchange fused into the epilogue (GemmXDev in common.cuh).
+template <int BM, int BN, int WM, int WN, int STAGES, int MINB, int RC, int RP, int XMODE>
 __global__ void __launch_bounds__(((BM / WM) * (BN / WN) + 4) * 32, MINB)
-    gemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmParams p) {
+    gemm_tn_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   constexpr int NWM = BM / WM, NWN = BN / WN, NCW = NWM * NWN;
   constexpr int FM = WM / 8, FN = WN / 8;
   constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
 
+  extern __shared__ uint8_t smem_raw[];
   const int flags = p.flags;
+  const int gm = p.gm, gn = p.gn;
+  // Which tile?  Plain launches: the linear CTA id.  Mode 1: a ticket (CTAs start in ticket order whatever order the hardware
+  // dispatches them in); tickets [0, T) walk the tiles this layer does NOT own, [T, 2T) the ones it owns -- a ticket whose tile
+  // is of the other kind is a no-op.
+  int lin = (int)(blockIdx.x + gridDim.x * blockIdx.y);
+  bool owned_phase = false;
+  if (XMODE == 1) {
+    unsigned int* tk = reinterpret_cast<unsigned int*>(smem_raw);
+    const int T = gm * gn;
+    if (threadIdx.x == 0) {
+      const unsigned int mine = atomicAdd(p.x.ticket, 1u);
+      if (mine == 2u * (unsigned)T - 1u) *p.x.ticket = 0u;  // last ticket of this launch: re-arm the counter for the next product of the stream
+      *tk = mine;
+    }
+    __syncthreads();
+    const int t = (int)*tk;
+    __syncthreads();  // smem_raw is reused below
+    owned_phase = t >= T;
+    lin = owned_phase ? t - T : t;
+  }
   // Longest-tile-first over the WHOLE grid: with a triangular operand the k extent depends on one tile coordinate only, so the
   // linear CTA id is mapped to tiles in order of decreasing k extent (row-major over the other coordinate).  The first wave then
   // holds the longest tiles and second residents / the tail get the short ones (a per-column reversal alone interleaves long and
   // short tiles and lets two long tiles share an SM).
-  const int lin = (int)(blockIdx.x + gridDim.x * blockIdx.y);
   int tm, tn;
-  if (flags & CAPITAL_GEMM_A_UPPER) { tm = (int)gridDim.x - 1 - lin / (int)gridDim.y; tn = lin % (int)gridDim.y; }
-  else if (flags & CAPITAL_GEMM_B_UPPER) { tn = (int)gridDim.y - 1 - lin / (int)gridDim.x; tm = lin % (int)gridDim.x; }
-  else if (flags & CAPITAL_GEMM_A_LOWER) { tm = lin / (int)gridDim.y; tn = lin % (int)gridDim.y; }
-  else if (flags & CAPITAL_GEMM_B_LOWER) { tn = lin / (int)gridDim.x; tm = lin % (int)gridDim.x; }
-  else { tm = (int)blockIdx.x; tn = (int)blockIdx.y; }
+  if (flags & CAPITAL_GEMM_A_UPPER) { tm = gm - 1 - lin / gn; tn = lin % gn; }
+  else if (flags & CAPITAL_GEMM_B_UPPER) { tn = gn - 1 - lin / gm; tm = lin % gm; }
+  else if (flags & CAPITAL_GEMM_A_LOWER) { tm = lin / gn; tn = lin % gn; }
+  else if (flags & CAPITAL_GEMM_B_LOWER) { tn = lin / gm; tm = lin % gm; }
+  else { tm = lin % gm; tn = lin / gm; }
+  bool owner = true;
+  if (XMODE == 1) {
+    owner = ((tm + tn) % p.x.c) == p.x.z;
+    if (owner != owned_phase) return;
+  }
+  if (XMODE == 2 && (tn % p.x.c) != p.x.z) return;  // another layer computes this tile column and stores it here
   const int m0 = tm * BM, n0 = tn * BN;
   const int n0g = n0 + p.noff;  // column position used by the structure tests
   if ((flags & CAPITAL_GEMM_C_UPPER) && m0 > n0g + BN - 1) return;  // tile strictly below the diagonal
@@ -100,7 +151,7 @@ __global__ void __launch_bounds__(((BM / WM) * (BN / WN) + 4) * 32, MINB)
   if (flags & CAPITAL_GEMM_B_LOWER) kb = max(kb, n0g - p.koff);
   kb &= ~(BK - 1);
   int nk = ke > kb ? (ke - kb + BK - 1) / BK : 0;
-  if (nk == 0 && p.beta == 1.0 && p.ksplit <= 1) return;  // nothing to add (k-chunk entirely outside the operand's triangle)
+  if (nk == 0 && p.beta == 1.0 && p.ksplit <= 1) return;  // nothing to add (k-chunk entirely outside the operand's triangle); same on every layer
   if (p.ksplit > 1) {  // this CTA's contiguous chunk of k tiles
     const int per = (nk + p.ksplit - 1) / p.ksplit;
     const int t0 = min(nk, (int)blockIdx.z * per), t1 = min(nk, t0 + per);
@@ -108,8 +159,8 @@ __global__ void __launch_bounds__(((BM / WM) * (BN / WN) + 4) * 32, MINB)
     nk = t1 - t0;
     if (nk == 0) return;
   }
+  const int niter = nk * p.ncls;  // the k tiles of every operand class, one after the other
 
-  extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle, computed as an OFFSET into the shared array so that the pointer keeps its
   // shared address space (fragment loads then compile to LDS.128 instead of generic LD.E.128)
   const uint32_t raw_u32 = smem_u32(smem_raw);
@@ -133,14 +184,19 @@ __global__ void __launch_bounds__(((BM / WM) * (BN / WN) + 4) * 32, MINB)
     // ---------------- TMA producer warpgroup ----------------
     if (RC > 0) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(RP));
     if (warp == NCW && lane == 0) {
-      for (int it = 0; it < nk; it++) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(empty0 + s * 8, ph ^ 1);
-        mbar_expect_tx(full0 + s * 8, STAGE_BYTES);
-        const int kk = kb + it * BK;
-        tma_load_2d(smem_base + s * STAGE_BYTES, &mapA, full0 + s * 8, p.rowoffA + kk, m0);
-        tma_load_2d(smem_base + s * STAGE_BYTES + A_BYTES, &mapB, full0 + s * 8, p.rowoffB + kk, n0);
+      int it = 0;
+      for (int cls = 0; cls < p.ncls; cls++) {
+        const CUtensorMap* ma = cls ? &maps.a[1] : &maps.a[0];
+        const CUtensorMap* mb = cls ? &maps.b[1] : &maps.b[0];
+        for (int j = 0; j < nk; j++, it++) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(empty0 + s * 8, ph ^ 1);
+          mbar_expect_tx(full0 + s * 8, STAGE_BYTES);
+          const int kk = kb + j * BK;
+          tma_load_2d(smem_base + s * STAGE_BYTES, ma, full0 + s * 8, p.rowoffA + kk, m0);
+          tma_load_2d(smem_base + s * STAGE_BYTES + A_BYTES, mb, full0 + s * 8, p.rowoffB + kk, n0);
+        }
       }
     }
     return;
@@ -160,7 +216,7 @@ __global__ void __launch_bounds__(((BM / WM) * (BN / WN) + 4) * 32, MINB)
   const int b_row_off = A_BYTES + (wn * WN + g) * 128;
   const int swz[2] = {((2 * q) ^ g) * 16, ((2 * q + 1) ^ g) * 16};
 
-  for (int it = 0; it < nk; it++) {
+  for (int it = 0; it < niter; it++) {
     const int s = it % STAGES;
     const uint32_t ph = (it / STAGES) & 1;
     mbar_wait(full0 + s * 8, ph);
@@ -185,7 +241,48 @@ __global__ void __launch_bounds__(((BM / WM) * (BN / WN) + 4) * 32, MINB)
     if (lane == 0) mbar_arrive(empty0 + s * 8);
   }
 
-  // ---------------- epilogue: C = alpha * acc + beta * C ----------------
+  // ---------------- depth exchange, mode 1: partial tiles travel in fragment order ----------------
+  const int nother = (XMODE != 0) ? p.x.c - 1 : 0;
+  if (XMODE == 1) {
+    constexpr int NCT = NCW * 32;
+    const int ctid = threadIdx.x;  // consumer warps are warps 0 .. NCW-1
+    const long long tile_id = (long long)tm + (long long)gm * tn;
+    const long long tile_off = tile_id * (long long)(BM * BN);
+    if (!owner) {
+      const int zo = (tm + tn) % p.x.c, oi = zo < p.x.z ? zo : zo - 1;
+      double2* dst = reinterpret_cast<double2*>(p.x.precv_peer[oi] + tile_off);
+#pragma unroll
+      for (int i = 0; i < FM; i++)
+#pragma unroll
+        for (int j = 0; j < FN; j++) dst[(i * FN + j) * NCT + ctid] = make_double2(acc[i][j][0], acc[i][j][1]);
+      __threadfence_system();
+      consumer_bar(NCT);
+      if (ctid == 0) st_release_sys(p.x.tflag_peer[oi] + tile_id, p.x.seq);
+      return;
+    }
+    for (int oi = 0; oi < nother; oi++) {
+      if (ctid == 0) {
+        const unsigned long long* f = p.x.tflag_local[oi] + tile_id;
+        const unsigned long long t0 = globaltimer_ns();
+        while (ld_acquire_sys(f) < p.x.seq) {
+          __nanosleep(64);
+          if (globaltimer_ns() - t0 > 20000000000ull) { atomicExch(p.x.err, -1); break; }  // 20 s: a peer died; report instead of hanging
+        }
+      }
+      consumer_bar(NCT);
+      const double2* src = reinterpret_cast<const double2*>(p.x.precv_local[oi] + tile_off);
+#pragma unroll
+      for (int i = 0; i < FM; i++)
+#pragma unroll
+        for (int j = 0; j < FN; j++) {
+          const double2 v = __ldcg(src + (i * FN + j) * NCT + ctid);
+          acc[i][j][0] += v.x;
+          acc[i][j][1] += v.y;
+        }
+    }
+  }
+
+  // ---------------- epilogue: C = alpha * acc + beta * C (to every replica when the exchange is on) ----------------
   const double alpha = p.alpha, beta = p.beta;
   const bool upper_only = flags & CAPITAL_GEMM_C_UPPER;
 #pragma unroll
@@ -194,26 +291,33 @@ __global__ void __launch_bounds__(((BM / WM) * (BN / WN) + 4) * 32, MINB)
     for (int e = 0; e < 2; e++) {
       const int col = n0 + wn * WN + j * 8 + 2 * q + e;
       if (col >= p.N) continue;
-      double* cc = p.C + (long long)col * p.ldc;
+      const long long coff = (long long)col * p.ldc;
+      double* cc = p.C + coff;
 #pragma unroll
       for (int i = 0; i < FM; i++) {
         const int row = m0 + wm * WM + i * 8 + g;
         if (row >= p.M || (upper_only && row > col + p.noff)) continue;
         double v = alpha * acc[i][j][e];
-        if (p.ksplit > 1) { atomicAdd(cc + row, v); continue; }
+        if (XMODE == 0 && p.ksplit > 1) { atomicAdd(cc + row, v); continue; }
         if (beta != 0.0) v += beta * cc[row];
         cc[row] = v;
+        if (XMODE != 0) {
+          for (int oi = 0; oi < nother; oi++) p.x.Cpeer[oi][coff + row] = v;
+        }
       }
     }
   }
+  if (XMODE != 0) __threadfence_system();  // the replicas' stores are performed before the kernel retires (the done flag follows on the stream)
 }
 
-template <int BM, int BN, int WM, int WN, int STAGES, int MINB, int RC, int RP>
+template <int BM_, int BN_, int WM, int WN, int STAGES, int MINB, int RC, int RP>
 struct GemmCfg {
-  static_assert(((BM / WM) * (BN / WN)) % 4 == 0, "consumer warps must form whole warpgroups");
+  static_assert(((BM_ / WM) * (BN_ / WN)) % 4 == 0, "consumer warps must form whole warpgroups");
+  static constexpr int BM = BM_, BN = BN_;
   static constexpr int threads = ((BM / WM) * (BN / WN) + 4) * 32;
   static constexpr int smem = STAGES * (BM + BN) * 128 + 2 * STAGES * 8 + 1024;
-  static constexpr auto kernel = gemm_tn_kernel<BM, BN, WM, WN, STAGES, MINB, RC, RP>;
+  template <int XMODE>
+  static constexpr auto kernel() { return gemm_tn_kernel<BM, BN, WM, WN, STAGES, MINB, RC, RP, XMODE>; }
 };
 using CfgBig = GemmCfg<128, 128, 64, 32, 5, 1, 232, 40>;   // 8 consumer warps + producer group, 1 CTA / SM
 using CfgSmall = GemmCfg<64, 64, 32, 32, 6, 2, 0, 0>;       // 4 consumer warps + producer group, 2 CTAs / SM
@@ -235,47 +339,83 @@ capital_status_t make_map(capital_ctx* ctx, CUtensorMap* map, const double* base
   return CAPITAL_OK;
 }
 
-template <class Cfg, int BM, int BN>
-capital_status_t launch(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
-                        int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags, int ksplit, int koff = 0, int noff = 0) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    CAP_CUDA(cudaFuncSetAttribute(Cfg::kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem));
-    attr_set = true;
-  }
-  GemmParams p;
+template <class Cfg>
+capital_status_t launch(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, GemmOperands ops, double beta, double* C,
+                        int64_t ldc, int flags, int ksplit, int koff, int noff, const GemmXDev* x) {
+  constexpr int BM = Cfg::BM, BN = Cfg::BN;
+  GemmParams p{};
   p.M = (int)m; p.N = (int)n; p.K = (int)k; p.flags = flags; p.alpha = alpha; p.beta = beta; p.C = C; p.ldc = ldc; p.ksplit = ksplit; p.koff = koff; p.noff = noff;
+  p.ncls = ops.ncls;
   // TMA fetches 16-byte granules: a window that starts on an odd row (8-byte aligned only) cannot be addressed by
   // box coordinates, so it is first copied to an aligned scratch (O(k m) bytes against O(k m n) flops; only odd
   // split points of non-power-of-two sizes ever take this path).
-  const bool same = (A == B && lda == ldb && m == n);
-  if ((uintptr_t)A & 15) {
-    double* sc;
+  const char* sfx = st == ctx->side ? "_side" : "";
+  int64_t la[GEMM_NCLS_MAX], lb[GEMM_NCLS_MAX];
+  for (int c = 0; c < ops.ncls; c++) {
+    la[c] = ops.lda; lb[c] = ops.ldb;
+    const bool same = (ops.A[c] == ops.B[c] && ops.lda == ops.ldb && m == n);
     const int64_t lds = round_up(k, 2);
-    CAP_TRY(ctx->workspace(st == ctx->side ? "gemm_alignA_side" : "gemm_alignA", (size_t)lds * m * 8, (void**)&sc));
-    CAP_TRY(copy_block(ctx, st, k, m, A, lda, sc, lds));
-    if (same) { B = sc; ldb = lds; }
-    A = sc; lda = lds;
-  }
-  if ((uintptr_t)B & 15) {
-    double* sc;
-    const int64_t lds = round_up(k, 2);
-    CAP_TRY(ctx->workspace(st == ctx->side ? "gemm_alignB_side" : "gemm_alignB", (size_t)lds * n * 8, (void**)&sc));
-    CAP_TRY(copy_block(ctx, st, k, n, B, ldb, sc, lds));
-    B = sc; ldb = lds;
+    if ((uintptr_t)ops.A[c] & 15) {
+      double* sc;
+      CAP_TRY(ctx->workspace(std::string("gemm_alignA") + sfx + std::to_string(c), (size_t)lds * m * 8, (void**)&sc));
+      CAP_TRY(copy_block(ctx, st, k, m, ops.A[c], ops.lda, sc, lds));
+      if (same) { ops.B[c] = sc; lb[c] = lds; }
+      ops.A[c] = sc; la[c] = lds;
+    }
+    if ((uintptr_t)ops.B[c] & 15) {
+      double* sc;
+      CAP_TRY(ctx->workspace(std::string("gemm_alignB") + sfx + std::to_string(c), (size_t)lds * n * 8, (void**)&sc));
+      CAP_TRY(copy_block(ctx, st, k, n, ops.B[c], ops.ldb, sc, lds));
+      ops.B[c] = sc; lb[c] = lds;
+    }
   }
   p.rowoffA = 0;
   p.rowoffB = 0;
-  CUtensorMap mapA, mapB;
-  CAP_TRY(make_map(ctx, &mapA, A, k, m, lda, BK, BM));
-  CAP_TRY(make_map(ctx, &mapB, B, k, n, ldb, BK, BN));
-  dim3 grid((unsigned)ceil_div(m, BM), (unsigned)ceil_div(n, BN), (unsigned)ksplit);
-  Cfg::kernel<<<grid, Cfg::threads, Cfg::smem, st>>>(mapA, mapB, p);
+  GemmMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  for (int c = 0; c < ops.ncls; c++) {
+    CAP_TRY(make_map(ctx, &maps.a[c], ops.A[c], k, m, la[c], BK, BM));
+    CAP_TRY(make_map(ctx, &maps.b[c], ops.B[c], k, n, lb[c], BK, BN));
+  }
+  p.gm = (int)ceil_div(m, BM); p.gn = (int)ceil_div(n, BN);
+  const int xmode = x ? x->mode : 0;
+  if (xmode) p.x = *x;
+  if (xmode == 1) {
+    dim3 grid((unsigned)(2 * p.gm * p.gn), 1, 1);
+    Cfg::template kernel<1>()<<<grid, Cfg::threads, Cfg::smem, st>>>(maps, p);
+  } else if (xmode == 2) {
+    dim3 grid((unsigned)p.gm, (unsigned)p.gn, 1);
+    Cfg::template kernel<2>()<<<grid, Cfg::threads, Cfg::smem, st>>>(maps, p);
+  } else {
+    dim3 grid((unsigned)p.gm, (unsigned)p.gn, (unsigned)ksplit);
+    Cfg::template kernel<0>()<<<grid, Cfg::threads, Cfg::smem, st>>>(maps, p);
+  }
   CAP_CUDA(cudaGetLastError());
   return CAPITAL_OK;
 }
 
 }  // namespace
+
+// Per-device kernel attributes (the >48 KB dynamic shared memory opt-in is a per-device property): called from capital_create
+// after cudaSetDevice, so that every context's device is prepared whatever the process did before.
+capital_status_t gemm_tn_init(capital_ctx* ctx) {
+  CAP_CUDA(cudaFuncSetAttribute(CfgBig::kernel<0>(), cudaFuncAttributeMaxDynamicSharedMemorySize, CfgBig::smem));
+  CAP_CUDA(cudaFuncSetAttribute(CfgBig::kernel<1>(), cudaFuncAttributeMaxDynamicSharedMemorySize, CfgBig::smem));
+  CAP_CUDA(cudaFuncSetAttribute(CfgBig::kernel<2>(), cudaFuncAttributeMaxDynamicSharedMemorySize, CfgBig::smem));
+  CAP_CUDA(cudaFuncSetAttribute(CfgSmall::kernel<0>(), cudaFuncAttributeMaxDynamicSharedMemorySize, CfgSmall::smem));
+  CAP_CUDA(cudaFuncSetAttribute(CfgSmall::kernel<1>(), cudaFuncAttributeMaxDynamicSharedMemorySize, CfgSmall::smem));
+  CAP_CUDA(cudaFuncSetAttribute(CfgSmall::kernel<2>(), cudaFuncAttributeMaxDynamicSharedMemorySize, CfgSmall::smem));
+  return CAPITAL_OK;
+}
+
+// which tile configuration a product of this output shape runs with (the same on every layer: exchange buffers are tile-indexed)
+static inline bool gemm_uses_big(const capital_ctx* ctx, int64_t m, int64_t n) { return ceil_div(m, 128) * ceil_div(n, 128) >= ctx->num_sms; }
+void gemm_tn_xsizes(const capital_ctx* ctx, int64_t m, int64_t n, size_t* precv_bytes, size_t* tiles) {
+  const int64_t b = gemm_uses_big(ctx, m, n) ? 128 : 64;
+  const int64_t t = ceil_div(m, b) * ceil_div(n, b);
+  *tiles = (size_t)t;
+  *precv_bytes = (size_t)t * b * b * 8;
+}
 
 // Split-K variant for short-and-fat products (the tall-skinny Gram matrix, cacqr.hpp:15): C += alpha A^T B with the
 // k range cut into `ksplit` chunks, partial tiles accumulated with FP64 atomics.  C must hold the addend on entry.
@@ -291,8 +431,9 @@ capital_status_t gemm_tn_splitk(capital_ctx* ctx, cudaStream_t st, int64_t m, in
   ctx->counters.kernel_launches++;
   ctx->counters.gemm_launches++;
   ctx->counters.gemm_flops += 2.0 * (double)m * (double)n * (double)k * ((flags & CAPITAL_GEMM_C_UPPER) ? 0.5 : 1.0);
-  if (ks == 1) return launch<CfgSmall, 64, 64>(ctx, st, m, n, k, alpha, A, lda, B, ldb, 1.0, C, ldc, flags, 1);
-  return launch<CfgSmall, 64, 64>(ctx, st, m, n, k, alpha, A, lda, B, ldb, 1.0, C, ldc, flags, (int)ks);
+  GemmOperands ops;
+  ops.A[0] = A; ops.B[0] = B; ops.lda = lda; ops.ldb = ldb;
+  return launch<CfgSmall>(ctx, st, m, n, k, alpha, ops, 1.0, C, ldc, flags, (int)ks, 0, 0, nullptr);
 }
 
 // Same product issued as a sequence of k-chunked launches (C accumulates).  Used for deferred work on the low-priority
@@ -316,16 +457,28 @@ capital_status_t gemm_tn(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n
 
 capital_status_t gemm_tn_off(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
                              int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags, int koff, int noff) {
+  GemmOperands ops;
+  ops.A[0] = A; ops.B[0] = B; ops.lda = lda; ops.ldb = ldb;
+  return gemm_tn_x(ctx, st, m, n, k, alpha, ops, beta, C, ldc, flags, koff, noff, nullptr);
+}
+
+// General form: `ops.ncls` operand classes, optional fused depth exchange (see GemmXDev).  With an exchange every layer must call
+// this with the same shapes and flags (the tile grid and the tile ownership are functions of them only).
+capital_status_t gemm_tn_x(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const GemmOperands& ops,
+                           double beta, double* C, int64_t ldc, int flags, int koff, int noff, const GemmXDev* x) {
   if (m <= 0 || n <= 0) return CAPITAL_OK;
-  if (k < 0 || lda < k || ldb < k || ldc < m || (lda & 1) || (ldb & 1) || ((uintptr_t)A & 7) || ((uintptr_t)B & 7)) {
+  bool bad = k < 0 || ops.lda < k || ops.ldb < k || ldc < m || (ops.lda & 1) || (ops.ldb & 1) || ops.ncls < 1 || ops.ncls > GEMM_NCLS_MAX;
+  for (int c = 0; !bad && c < ops.ncls; c++) bad = !ops.A[c] || !ops.B[c] || ((uintptr_t)ops.A[c] & 7) || ((uintptr_t)ops.B[c] & 7);
+  if (bad) {
     ctx->set_error("gemm_tn: invalid/unsupported leading dimensions (lda, ldb must be even and >= k)");
     return CAPITAL_ERR_INVALID;
   }
   if (k == 0) { ctx->set_error("gemm_tn: k must be positive"); return CAPITAL_ERR_INVALID; }
   if (m >= (1LL << 31) || n >= (1LL << 31) || k >= (1LL << 31) - 16) return CAPITAL_ERR_INVALID;
+  if (x && x->mode && (x->c < 2 || x->c - 1 > GEMM_XPEERS_MAX)) { ctx->set_error("gemm_tn: exchange over more than 4 layers"); return CAPITAL_ERR_UNSUPPORTED; }
   ctx->counters.kernel_launches++;
   ctx->counters.gemm_launches++;
-  // algorithmic flops of this product (structure exploited exactly, not tile-rounded)
+  // algorithmic flops of this product on THIS device (structure exploited exactly, not tile-rounded)
   double f = 2.0 * (double)m * (double)n * (double)k;
   const bool atri = flags & (CAPITAL_GEMM_A_UPPER | CAPITAL_GEMM_A_LOWER), btri = flags & (CAPITAL_GEMM_B_UPPER | CAPITAL_GEMM_B_LOWER);
   if (atri && btri) f = 2.0 * (double)m * (double)n * (double)k / 3.0;
@@ -333,21 +486,22 @@ capital_status_t gemm_tn_off(capital_ctx* ctx, cudaStream_t st, int64_t m, int64
   else if (btri && (flags & CAPITAL_GEMM_B_UPPER) && noff > 0 && koff == 0 && k >= noff + n) f = (double)m * (double)n * (double)(2 * (int64_t)noff + n + 1);
   else if (btri) f = (double)m * (double)n * (double)(n + 1);
   else if (flags & CAPITAL_GEMM_C_UPPER) f = (double)k * (double)m * (double)(m + 1);
+  f *= ops.ncls;
+  if (x && x->mode == 2) f /= x->c;  // this layer computes every c-th tile column
   ctx->counters.gemm_flops += f;
-  const int64_t tiles_big = ceil_div(m, 128) * ceil_div(n, 128);
-  if (tiles_big >= ctx->num_sms) {
+  if (gemm_uses_big(ctx, m, n)) {
     // dominant kernel: optionally bracketed by events on its own stream (capital_profile_begin/end)
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ctx->profiling) {
       CAP_TRY(ctx->prof_event(&e0)); CAP_TRY(ctx->prof_event(&e1));
       CAP_CUDA(cudaEventRecord(e0, st));
     }
-    CAP_TRY((launch<CfgBig, 128, 128>(ctx, st, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags, 1, koff, noff)));
+    CAP_TRY((launch<CfgBig>(ctx, st, m, n, k, alpha, ops, beta, C, ldc, flags, 1, koff, noff, x)));
     if (ctx->profiling) {
       CAP_CUDA(cudaEventRecord(e1, st));
       ctx->prof_recs.push_back({e0, e1, f});
     }
     return CAPITAL_OK;
   }
-  return launch<CfgSmall, 64, 64>(ctx, st, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags, 1, koff, noff);
+  return launch<CfgSmall>(ctx, st, m, n, k, alpha, ops, beta, C, ldc, flags, 1, koff, noff, x);
 }

@@ -611,16 +611,22 @@ __global__ void __cluster_dims__(BC_CLUSTER, 1, 1) __launch_bounds__(256, 1)
 }
 }  // namespace
 
+namespace {
+constexpr int LEAF_SMEM = 3 * LEAF_MAX * LD * (int)sizeof(double);
+constexpr int BASECASE_SMEM = (4 * TILE_DOUBLES + 128 + 512 + 256) * (int)sizeof(double);
+}  // namespace
+// per-device shared-memory opt-in of the two kernels (called from capital_create after cudaSetDevice)
+capital_status_t leaf_init(capital_ctx* ctx) {
+  CAP_CUDA(cudaFuncSetAttribute(leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM));
+  CAP_CUDA(cudaFuncSetAttribute(basecase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BASECASE_SMEM));
+  return CAPITAL_OK;
+}
+
 capital_status_t leaf_cholinv(capital_ctx* ctx, cudaStream_t st, int nb, const double* W, int64_t ldw, double* R, int64_t ldr, double* Ri,
                               int64_t ldri, double* RiT, int64_t ldrit) {
   if (nb <= 0) return CAPITAL_OK;
   if (nb > LEAF_MAX) return CAPITAL_ERR_INVALID;
-  constexpr int smem = 3 * LEAF_MAX * LD * (int)sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CAP_CUDA(cudaFuncSetAttribute(leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  constexpr int smem = LEAF_SMEM;
   leaf_kernel<<<1, 256, smem, st>>>(nb, W, ldw, R, ldr, Ri, ldri, RiT, ldrit, ctx->d_info);
   ctx->counters.kernel_launches++;
   ctx->counters.leaf_launches++;
@@ -632,12 +638,7 @@ capital_status_t leaf_cholinv(capital_ctx* ctx, cudaStream_t st, int nb, const d
 capital_status_t basecase_cholinv(capital_ctx* ctx, cudaStream_t st, int nb, double* W, int64_t ldw, double* R, int64_t ldr, double* Ri,
                                   int64_t ldri, double* RiT, int64_t ldrit) {
   if (nb % 64 != 0 || nb < 64 || nb > BASECASE_MAX || RiT == nullptr) return CAPITAL_ERR_INVALID;
-  constexpr int smem = (4 * TILE_DOUBLES + 128 + 512 + 256) * (int)sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CAP_CUDA(cudaFuncSetAttribute(basecase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  constexpr int smem = BASECASE_SMEM;
   long long* dbg = nullptr;
   if (getenv("CAPITAL_BC_DEBUG")) {
     CAP_TRY(ctx->workspace("bc_dbg", 64 * sizeof(long long), (void**)&dbg));

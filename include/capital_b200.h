@@ -81,11 +81,23 @@ capital_status_t capital_create(capital_ctx** ctx, const capital_grid_t* grid, i
  * topology.h:84-94).  Not needed when grid.size == 1. */
 capital_status_t capital_comm_unique_id(void* out128);
 capital_status_t capital_comm_init(capital_ctx* ctx, const void* nccl_unique_id);
+/* Same, bootstrapped through a caller-supplied host allgather instead of NCCL (MPI_Allgather in an MPI program:
+ *   int ag(void* user, const void* send, void* recv, int64_t bytes) { return MPI_Allgather(send, bytes, MPI_BYTE, recv, bytes, MPI_BYTE, *(MPI_Comm*)user); }
+ * ).  The library only exchanges small blobs (IPC handles) through it, at init and when its peer-visible arena has to grow;
+ * matrix data never goes through it.  Must return 0 on success; recv holds size * bytes. */
+typedef int (*capital_allgather_fn)(void* user, const void* send, void* recv, int64_t bytes_per_rank);
+capital_status_t capital_comm_init_host(capital_ctx* ctx, capital_allgather_fn allgather, void* user);
 void capital_destroy(capital_ctx* ctx);
 const char* capital_last_error(const capital_ctx* ctx);
 capital_status_t capital_get_counters(const capital_ctx* ctx, capital_counters_t* out);
 capital_status_t capital_reset_counters(capital_ctx* ctx);
 capital_status_t capital_synchronize(capital_ctx* ctx);
+/* Rebind the context to another caller stream (cudaStream_t): later calls are enqueued on it, ordered after everything already
+ * enqueued on the previous stream.  The Python mirror calls it whenever torch's current stream changed. */
+capital_status_t capital_set_stream(capital_ctx* ctx, void* stream);
+/* policy::cholinv::FlushIntermediates (cholinv/policy.h:85-156): release every work buffer the context holds (the next factor call
+ * re-allocates: SaveIntermediates semantics -- keep them between calls -- are the default, cholinv/policy.h:20-83). */
+capital_status_t capital_release_workspace(capital_ctx* ctx);
 /* time (ms) between two library-recorded CUDA events bracketing the last factor call, on its stream */
 capital_status_t capital_last_factor_ms(const capital_ctx* ctx, float* ms);
 
@@ -96,6 +108,12 @@ capital_status_t capital_profile_begin(capital_ctx* ctx);
 /* enabled = 0 runs the recursion on a single stream (no deferred-update overlap): isolates per-kernel durations. */
 capital_status_t capital_set_overlap(capital_ctx* ctx, int enabled);
 capital_status_t capital_profile_end(capital_ctx* ctx, double* kernel_ms, double* kernel_flops, int64_t* launches);
+
+/* Test facility, no device needed: records the synchronisation-relevant operations (flag waits / signals, fused products, events,
+ * peer DMA, arena windows read / written) that rank `grid->rank` would enqueue for two consecutive cholinv::factor calls, 8 int64
+ * per record (kind, stream, a .. f); tests replay the traces of all ranks of a grid to prove the flag protocol cannot deadlock. */
+capital_status_t capital_dist_trace_cholinv(const capital_grid_t* grid, int64_t n_global, const capital_cholinv_args_t* args,
+                                            int64_t* out, int64_t cap_records, int64_t* n_records);
 
 /* ---- generators (device kernels; bit-exact with the reference's drand48-based ones) ---------- */
 /* matrix::distribute_symmetric(x, y, d, d, key, diagonallyDominant) -- structure.hpp:69-103. */

@@ -23,8 +23,14 @@ def load(name):
 
 def main():
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(lr)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    same_dev = bool(os.environ.get("CAPITAL_MP_SAME_DEVICE"))  # all ranks on cuda:0 (1-GPU boxes): same code path, time-sliced
+    small = same_dev or bool(os.environ.get("CAPITAL_MP_SMALL"))
+    if same_dev:
+        torch.cuda.set_device(0)
+        dist.init_process_group("gloo")
+    else:
+        torch.cuda.set_device(lr)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
     ok = True
     msgs = []
     if world == 8:
@@ -44,7 +50,7 @@ def main():
             ok &= er < 1e-13 and ei < 1e-13 and same_zeros and res < 1e-14
             msgs.append(f"{name}: dR={er:.1e} dRinv={ei:.1e} zeros={same_zeros} res={res:.1e}")
         # --- oracle restatement at a size with several distributed levels + ragged local sizes ---
-        for n, ci, bcm in ((1024, 1, -2), (1536, 0, -3), (4096, 0, -3)):
+        for n, ci, bcm in (((768, 1, -2), (1536, 0, -3)) if small else ((1024, 1, -2), (1536, 0, -3), (4096, 0, -3))):
             A = cb.matrix(n, n, 2, 2).distribute_symmetric(topo)
             args = cb.cholinv.info(ci, 1, bcm, "U")
             cb.cholinv.factor(A, args, topo)
@@ -63,7 +69,7 @@ def main():
         c = 2 if world == 2 else 1
         topo = cb.topo.square(world, rank, c)
         d = topo.d
-        sizes = ((512, 1, -2), (2048, 0, -3), (3072, 1, -3)) + (((8192, 1, -4),) if os.environ.get("CAPITAL_DIST_PIPELINE") else ())
+        sizes = ((512, 1, -2), (1536, 0, -3)) if small else ((512, 1, -2), (2048, 0, -3), (3072, 1, -3), (8192, 1, -4))
         for n, ci, bcm in sizes:
             A = cb.matrix(n, n, d, d).distribute_symmetric(topo)
             args = cb.cholinv.info(ci, 1, bcm, "U")
@@ -82,7 +88,7 @@ def main():
         c = {2: 2, 4: 1, 8: 2}[world]
         topo = cb.topo.square(world, rank, c)
         d = topo.d
-        for n, ci in ((4096 * d, 0), (2048 * d, 1)):
+        for n, ci in (((2048 * d, 0),) if small else ((4096 * d, 0), (2048 * d, 1))):
             A = cb.matrix(n, n, d, d).distribute_symmetric(topo)
             dev = cb.cholinv.info(ci, 1, -3, "U")
             cb.cholinv.factor(A, dev, topo)
@@ -92,6 +98,25 @@ def main():
             same = torch.equal(hst.R, dev.R.cpu()) and torch.equal(hst.Rinv, dev.Rinv.cpu())
             ok &= same and not hst.R.is_cuda
             msgs.append(f"host path n={n} ci={ci}: identical={same}")
+    if world == 8 and not small:
+        # --- the distributed result against the single-GPU one at a size with big products (the generator is grid-independent) ---
+        n = 8192
+        topo = cb.topo.square(8, rank, 2)
+        A = cb.matrix(n, n, 2, 2).distribute_symmetric(topo)
+        args = cb.cholinv.info(0, 1, -3, "U")
+        cb.cholinv.factor(A, args, topo)
+        t1 = cb.topo.square(1, 0, 1)
+        A1 = cb.matrix(n, n, 1, 1).distribute_symmetric(t1)
+        a1 = cb.cholinv.info(0, 1, -3, "U", serialize=False)
+        cb.cholinv.factor(A1, a1, t1)
+        R1, Ri1 = cb.cholinv.construct_R(a1), cb.cholinv.construct_Rinv(a1)
+        R, Ri = cb.cholinv.construct_R(args), cb.cholinv.construct_Rinv(args)
+        sel = (slice(topo.y, None, 2), slice(topo.x, None, 2))
+        er = ((R - torch.triu(R1[sel])).abs().max() / R1.abs().max()).item()
+        ei = ((Ri - torch.triu(Ri1[sel])).abs().max() / Ri1.abs().max()).item()
+        ok &= er < 2e-13 and ei < 2e-13
+        msgs.append(f"8 GPUs vs 1 GPU n={n}: dR={er:.1e} dRinv={ei:.1e}")
+        del A1, a1, R1, Ri1
     if world in (2, 4, 8):
         # --- SUMMA GEMM entry point (T*N) on the same grid, against the global product ---
         c = {2: 2, 4: 1, 8: 2}[world]
@@ -134,7 +159,7 @@ def main():
         res, orth = cb.cacqr.validate(A, qa, qt)
         ok &= er < 1e-12 and eq < 1e-12 and res < 1e-14 and orth < 1e-15
         msgs.append(f"cacqr golden: dR={er:.1e} dQ={eq:.1e} res={res:.1e} orth={orth:.1e}")
-    m, n = 1 << 17, 128
+    m, n = (1 << 13, 64) if small else (1 << 17, 128)
     A = cb.matrix(n, m, 1, world).distribute_random(qt, rank)
     qa = cb.cacqr.info(2, cb.cholinv.info(0, 1, 0, "U"))
     cb.cacqr.factor(A, qa, qt)

@@ -1,8 +1,8 @@
 """The block-wise output of the experimental CAPITAL_ZC_OUT path must write every slot of the packed triangles exactly once
-(host mirror of the `block_done` calls in cholinv_local.cu: capital_b200/schedule.py::emission_blocks)."""
+(host mirror of the `block_done` calls in cholinv_local.cu: tests/host_mirror.py::emission_blocks)."""
 import numpy as np
 import pytest
-from capital_b200 import schedule as sch
+import host_mirror as sch
 
 
 @pytest.mark.parametrize("n,bc,split,ci,depth", [(16384, 512, 1, 0, 3), (16384, 512, 1, 1, 3), (8192, 512, 1, 1, 2), (9088, 568, 1, 1, 3),

@@ -55,6 +55,55 @@ def test_cholinv_matches_oracle(topo, n, ci, bcm, serialize):
     assert res <= 1e-12 and abs(res - co.cholesky_residual(a, R)) < 1e-15
 
 
+@pytest.mark.parametrize("n", [512, 2000])
+@pytest.mark.parametrize("serialize", [True, False])
+def test_cholinv_whole_matrix_is_the_reference_base_case(topo, n, serialize):
+    """bc_mult_dim >= 0 on one rank: n <= bcDimension, so the reference's invoke goes straight to its base case (potrf + trtri of the
+    whole block, cholinv.hpp:93-104) and returns the FULL inverse even when complete_inv == 0 -- nothing is skipped, nothing stale."""
+    A = cb.matrix(n, n, 1, 1).distribute_symmetric(topo)
+    junk = cb.cholinv.info(1, 1, -3, "U", serialize=serialize)  # fills the work buffers with the values of another schedule first
+    cb.cholinv.factor(A, junk, topo)
+    args = cb.cholinv.info(0, 1, 0, "U", serialize=serialize)
+    args.R = torch.full_like(junk.R, float("nan"))
+    args.Rinv = torch.full_like(junk.Rinv, float("nan"))
+    cb.cholinv.factor(A, args, topo)
+    a = co.spd_global(n)
+    r_o, ri_o = co.cholinv(a, False, 1, co.bc_dimension(n, 1, 1, 0))
+    assert np.count_nonzero(np.triu(ri_o, 1)) > n * (n - 1) // 2 - 8  # the oracle (= reference) inverse is full
+    R = cb.cholinv.construct_R(args, topo).cpu().numpy()
+    Ri = cb.cholinv.construct_Rinv(args, topo).cpu().numpy()
+    assert np.abs(R - r_o).max() <= 2e-13 * np.abs(r_o).max()
+    assert np.abs(Ri - ri_o).max() <= 2e-13 * np.abs(ri_o).max()
+
+
+def test_release_workspace_then_factor_again(topo):
+    """FlushIntermediates semantics (cholinv/policy.h:85-156): every work buffer can be dropped between calls."""
+    n = 1024
+    A = cb.matrix(n, n, 1, 1).distribute_symmetric(topo)
+    args = cb.cholinv.info(1, 1, -2, "U")
+    cb.cholinv.factor(A, args, topo)
+    keep = args.R.clone()
+    free0 = torch.cuda.mem_get_info()[0]
+    topo.context().release_workspace()
+    assert torch.cuda.mem_get_info()[0] > free0
+    cb.cholinv.factor(A, args, topo)
+    assert torch.equal(keep, args.R)
+
+
+def test_context_follows_the_current_torch_stream(topo):
+    n = 768
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        A = cb.matrix(n, n, 1, 1).distribute_symmetric(topo)
+        args = cb.cholinv.info(1, 1, -2, "U")
+        cb.cholinv.factor(A, args, topo)
+        assert cb.cholinv.residual(A, args, topo) < 1e-14
+    A2 = cb.matrix(n, n, 1, 1).distribute_symmetric(topo)  # back on the default stream
+    a2 = cb.cholinv.info(1, 1, -2, "U")
+    cb.cholinv.factor(A2, a2, topo)
+    assert torch.equal(a2.R, args.R)
+
+
 def test_cholinv_host_pointers_and_reuse(topo):
     """reference-facing call: pinned host buffers in, pinned host buffers out; repeated calls reuse the workspaces."""
     n = 640
