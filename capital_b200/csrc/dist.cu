@@ -421,6 +421,22 @@ capital_status_t product(Dist& D, int q, int64_t m, int64_t n, int64_t k, double
       }
     }
   }
+  // Flags of the depth handshake: ready(p) = 2 seq - 1 ("nothing I enqueued before product p still reads its C window"), done(p) =
+  // 2 seq ("my kernel has retired: my partials / final tiles are stored").  With the n split a layer stores final tiles into its
+  // partners' C without needing anything from them, so it must first know they are ready; with the k split an owner cannot finish
+  // a tile before the partner's kernel has started, which is the same guarantee for free.
+  auto handshake = [&](unsigned long long v) -> capital_status_t {
+    std::vector<Flag> s, ww;
+    for (int l = 0; l < D.c; l++) {
+      if (l == D.g.z) continue;
+      const int partner = rank_of(D.g, D.g.x, D.g.y, l);
+      s.push_back({partner, CTRL_DONE + (size_t)D.me * PEER_Q + q, v});
+      ww.push_back({D.me, CTRL_DONE + (size_t)partner * PEER_Q + q, v});
+    }
+    CAP_TRY(D.signal_flags(sid, s));
+    return D.wait_flags(sid, ww);
+  };
+  if (D.xmode == 2) CAP_TRY(handshake(2 * seq - 1));
   if (D.dry) {
     for (int j = 0; j < D.nk; j++) { D.rd(sid, ops.A[j], ops.lda, k, m); D.rd(sid, ops.B[j], ops.ldb, k, n); }
     const int64_t group = D.xmode ? (int64_t)(seq * 4 + q + 1) : 0;
@@ -429,18 +445,7 @@ capital_status_t product(Dist& D, int q, int64_t m, int64_t n, int64_t k, double
       if (l != D.g.z) D.wr(sid, rank_of(D.g, D.g.x, D.g.y, l), Cown, C.M->ld, m, n, group);
     D.rec(T_PRODUCT, sid, q, (int64_t)seq, D.xmode);
   } else CAP_TRY(gemm_tn_x(ctx, D.strm(sid), m, n, k, alpha, ops, beta, Cown, C.M->ld, flags, 0, noff, D.xmode ? &x : nullptr));
-  if (D.xmode) {
-    // my kernel has retired => my partials / final tiles have been stored; the partners' flags say the same about theirs
-    std::vector<Flag> s, ww;
-    for (int l = 0; l < D.c; l++) {
-      if (l == D.g.z) continue;
-      const int partner = rank_of(D.g, D.g.x, D.g.y, l);
-      s.push_back({partner, CTRL_DONE + (size_t)D.me * PEER_Q + q, seq});
-      ww.push_back({D.me, CTRL_DONE + (size_t)partner * PEER_Q + q, seq});
-    }
-    CAP_TRY(D.signal_flags(sid, s));
-    CAP_TRY(D.wait_flags(sid, ww));
-  }
+  if (D.xmode) CAP_TRY(handshake(2 * seq));  // my kernel has retired => my stores are performed; the partners' flags say the same about theirs
   return CAPITAL_OK;
 }
 
@@ -685,15 +690,15 @@ size_t cholinv_layout(Dist& D, char* base) {
 
 // reserve the arena for a layout; a layout the arena has not held before starts from zeros (mirror slots are only ever written
 // where a block is pushed; the triangular products read whole diagonal tiles and rely on zeros elsewhere)
-capital_status_t arena_prepare(Dist& D, size_t bytes, const std::string& signature) {
-  capital_ctx* ctx = D.ctx;
+capital_status_t arena_prepare(capital_ctx* ctx, size_t bytes, const std::string& signature) {
   CAP_TRY(peer_arena_reserve(ctx, bytes));
   if (ctx->arena_signature != signature) {
     // (every rank changes layout in the same call.)  A peer may still be pushing blocks of the previous layout that nobody waits
-    // for: all ranks drain first, then clear, and the start barrier of the call keeps new pushes behind everybody's clear.
+    // for: all ranks drain first, then clear, and a device barrier keeps new pushes behind everybody's clear.
     CAP_TRY(peer_host_barrier(ctx));
-    CAP_CUDA(cudaMemsetAsync(D.P->arena, 0, bytes, ctx->stream));
+    CAP_CUDA(cudaMemsetAsync(peer_of(ctx)->arena, 0, bytes, ctx->stream));
     ctx->arena_signature = signature;
+    if (ctx->grid.size > 1) CAP_TRY(peer_barrier(ctx, ctx->stream));  // nobody writes into a peer's arena before that peer has cleared it
   }
   return CAPITAL_OK;
 }
@@ -818,7 +823,7 @@ capital_status_t dist_cholinv_factor(capital_ctx* ctx, const double* A_local, in
   const size_t out_count = ostruct == CAPITAL_UPPERTRI_PACKED ? (size_t)L * (L + 1) / 2 : (size_t)L * L;
   CAP_CUDA(cudaEventRecord(ctx->ev_start, ctx->stream));
   const size_t bytes = cholinv_layout(D, nullptr);
-  CAP_TRY(arena_prepare(D, bytes, "cholinv:" + std::to_string(L) + ":" + std::to_string(D.bc_local) + ":" + std::to_string(D.split)));
+  CAP_TRY(arena_prepare(ctx, bytes, "cholinv:" + std::to_string(L) + ":" + std::to_string(D.bc_local) + ":" + std::to_string(D.split)));
   cholinv_layout(D, D.P->arena);
   CAP_TRY(bc_workspace(D));
   CAP_TRY(cap_stage_out_begin(ctx, R_local, out_count, "R_out", &D.dR));
@@ -891,7 +896,7 @@ capital_status_t dist_cholinv_residual(capital_ctx* ctx, const double* A_local, 
     return lay.off;
   };
   const size_t bytes = layout(nullptr);
-  CAP_TRY(arena_prepare(D, bytes, "cholres:" + std::to_string(L)));
+  CAP_TRY(arena_prepare(ctx, bytes, "cholres:" + std::to_string(L)));
   layout(D.P->arena);
   ctx->comm_used = 0;
   CAP_TRY(fork_streams(D));
@@ -965,7 +970,7 @@ capital_status_t dist_summa_gemm_tn(capital_ctx* ctx, int64_t m, int64_t n, int6
     return lay.off;
   };
   const size_t bytes = layout(nullptr);
-  CAP_TRY(arena_prepare(D, bytes, "summa:" + std::to_string(ml) + ":" + std::to_string(nl) + ":" + std::to_string(kl)));
+  CAP_TRY(arena_prepare(ctx, bytes, "summa:" + std::to_string(ml) + ":" + std::to_string(nl) + ":" + std::to_string(kl)));
   layout(D.P->arena);
   ctx->comm_used = 0;
   CAP_TRY(fork_streams(D));
@@ -1015,11 +1020,9 @@ capital_status_t sweep(Qr& q, double* Rout) {
 capital_status_t qr1d_arena(capital_ctx* ctx, int64_t count, double** ar) {
   *ar = nullptr;
   if (ctx->grid.size == 1) return CAPITAL_OK;
-  Dist D;
-  CAP_TRY(dist_setup(D, ctx, false));
   const size_t bytes = (size_t)2 * ctx->grid.size * count * 8 + 4096;
-  CAP_TRY(arena_prepare(D, bytes, "qr1d:" + std::to_string(count)));
-  *ar = (double*)D.P->arena;
+  CAP_TRY(arena_prepare(ctx, bytes, "qr1d:" + std::to_string(count)));
+  *ar = (double*)peer_of(ctx)->arena;
   return CAPITAL_OK;
 }
 }  // namespace
@@ -1091,7 +1094,7 @@ capital_status_t qr3_setup(capital_ctx* ctx, Dist& D, Qr3& q, int64_t m, int64_t
     qr3_layout(q, buf);
   } else {
     const size_t bytes = qr3_layout(q, nullptr);
-    CAP_TRY(arena_prepare(D, bytes, std::string(tag) + ":" + std::to_string(q.ml) + ":" + std::to_string(q.nl) + ":" + std::to_string(D.bc_local)));
+    CAP_TRY(arena_prepare(ctx, bytes, std::string(tag) + ":" + std::to_string(q.ml) + ":" + std::to_string(q.nl) + ":" + std::to_string(D.bc_local)));
     qr3_layout(q, D.P->arena);
   }
   CAP_TRY(bc_workspace(D));

@@ -104,7 +104,7 @@ int main() {
       const long long far_cycles = 4000000;  // ~2 ms per CTA
       if (mode) spin_kernel<<<148 * 4, 128, smem, fs>>>(far_cycles, nullptr);
       // give the far kernel time to occupy the machine
-      spin_kernel<<<1, 32, 0, chain>>>(400000, nullptr);
+      spin_kernel<<<1, 32, 1024, chain>>>(400000, nullptr);
       CK(cudaEventRecord(e0, chain));
       for (int i = 0; i < 10; i++) cluster_kernel<<<8, 256, 146 * 1024, chain>>>(20000, d_ids);
       CK(cudaEventRecord(e1, chain));
