@@ -4,14 +4,20 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n SIZE]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-A "step" is one cholinv::factor of the workload below on a resident (HBM) copy of the reference's own
-generator matrix (structure.hpp:69-103).  Rank 0 prints ONE JSON line.  `value` = whole-job n^3/3 / time
-("Cholesky TFLOP/s", the BASELINE.json metric); `e2e` repeats it through the public Python API with pinned HOST
-buffers (H2D of A and D2H of R, Rinv inside the timed region); `roofline` times the dominant kernel (128x128 DMMA
-GEMM) with CUDA events on its own stream inside the timed steps; `cpu_baseline` / `--impl reference` time the
-reference's own CPU implementation (oracle/_ref, built from /root/reference by oracle/build_ref.sh) on this box's
-host cores.  Workloads (BASELINE.json configs): N=1 n=16384 b=512 | N=8 n=65536 b=1024 on the reference's 2x2x2 grid;
-N=2 / N=4 are not valid reference grids (summa.hpp:16-31 needs c == d) and run the library's own 2x1x1 / 1x2x2 grids.
+A "step" is one cholinv::factor of the workload below on a resident (HBM) copy of the reference's own generator matrix
+(structure.hpp:69-103).  Rank 0 prints ONE JSON line.
+  value        whole-job n^3/3 / time ("Cholesky TFLOP/s", the BASELINE.json metric), CUDA events, max over ranks
+  e2e          the same through the public Python API with pinned HOST buffers (H2D of A and D2H of R, Rinv inside the timed region)
+  roofline     the dominant kernel (128x128 DMMA GEMM) timed with CUDA events on its own stream, against the FP64 tensor-pipe
+               peak MEASURED IN THIS RUN (capital_probe_dmma_f64) with the clocks sampled during it
+  parity       (N > 1) the distributed result against the reference's own per-rank dumps (tests/golden, 8 ranks) and against the
+               single-GPU factorization of the same matrix, before the timed region
+  cacqr        CholeskyQR2 (qr::cacqr::factor, 1D grid) on m = 2^17 rows per GPU x 256 columns: BASELINE config 4 at N = 8
+  strong       cholinv at a FIXED n = 32768 on the same N GPUs (the headline sizes grow with N)
+  cpu_baseline / --impl reference   the reference's own CPU implementation (oracle/_ref, built from /root/reference by
+               oracle/build_ref.sh) on this box's host cores.
+Workloads (BASELINE.json configs): N=1 n=16384 b=512 | N=8 n=65536 b=1024 on the reference's 2x2x2 grid; N=2 / N=4 are not valid
+reference grids (summa.hpp:16-31 needs c == d) and run the library's own 2x1x1 / 1x2x2 grids.
 """
 from __future__ import annotations
 import argparse, json, os, subprocess, sys, threading, time
@@ -19,13 +25,16 @@ import argparse, json, os, subprocess, sys, threading, time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-DMMA_PEAK_TFLOPS = 37.2  # measured on this pool's B200: profiles/r01_fp64_pipe_ceilings.log (DMMA.8x8x4, 148 SMs x 64 FMA/clk x 1.965 GHz)
+NOMINAL_DMMA_TFLOPS = 37.2  # 148 SMs x 64 FMA/clk x 1.965 GHz; only used when the in-run probe fails (said so in the line)
+HBM_GBS_FALLBACK = 6570.0
 WORKLOADS = {  # n_gpus -> (n, c, bc_mult_dim)  ; base-case size b = 512 (N=1) / 1024 (N=8) as in BASELINE.json configs
     1: (16384, 1, -5),
     2: (24576, 2, -5),
     4: (32768, 1, -5),
     8: (65536, 2, -4),
 }
+STRONG_N = 32768
+STRONG_BCM = {1: -6, 2: -5, 4: -5, 8: -3}  # base case 512 global (1024 on the 2x2x2 grid, as in BASELINE config 3)
 
 
 def clocks_sampler(stop: threading.Event, out: list, gpu_index: int):
@@ -54,8 +63,8 @@ def summarize_clocks(samples: list) -> dict:
             "samples": len(samples), "reasons": reasons}
 
 
-def ref_binary():
-    p = os.path.join(ROOT, "oracle", "_ref", "ref_cholinv")
+def ref_binary(name="ref_cholinv"):
+    p = os.path.join(ROOT, "oracle", "_ref", name)
     return p if os.path.exists(p) else None
 
 
@@ -81,7 +90,9 @@ def run_reference_cholinv(n: int, bc_mult: int, ranks: int, iters: int, timeout:
 
 
 def reference_arm(args):
-    """--impl reference: the reference's CPU path on this box's host cores, same metric/unit/config keys."""
+    """--impl reference: the reference's CPU path on this box's host cores, same metric/unit keys.  The reference allocates ~30x the
+    matrix, so the step is a BOUNDED SAMPLE: `config.n` is the size that actually ran, `config.full_workload_n` the size of
+    the GPU arm's workload at this N."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -89,22 +100,25 @@ def reference_arm(args):
     if args.n:
         n_full = args.n
     ranks = 1 if args.gpus == 1 else 8
-    n = min(n_full, 16384 if ranks == 1 else 8192)  # bounded sample: the reference allocates ~30x the matrix
-    bcm_s = bcm
+    n = min(n_full, 16384 if ranks == 1 else 8192)
     t0 = time.time()
-    iters = min(max(1, args.steps), 5)  # bounded: one reference factorization of the n=16384 sample takes ~10 s on 128 cores
-    d = run_reference_cholinv(n, bcm_s, ranks, iters, timeout=1500)
+    iters = min(max(1, args.steps), 3)  # one reference factorization of the n=16384 sample takes ~10 s on 128 cores
+    d = run_reference_cholinv(n, bcm, ranks, iters, timeout=1500)
     if not d or "time_mean_s" not in d:
         print(json.dumps({"impl": "reference", "unavailable": f"oracle/_ref/ref_cholinv missing or failed: {d}"}))
         return 0
     t = d["time_mean_s"]
     val = n ** 3 / 3 / t / 1e12
-    sample = (f"n={n} (full workload n={n_full}); {ranks} rank(s) x {d['threads_per_rank']} OpenBLAS threads; {iters} timed factorizations after "
-              f"one warm-up (bench/cholesky/cholinv.cpp protocol); reference validator residual {d['residual']:.2e}")
+    sample = (f"n={n} (GPU arm workload at this N: n={n_full}); {ranks} rank(s) x {d['threads_per_rank']} OpenBLAS threads; {iters} timed "
+              f"factorizations after one warm-up (bench/cholesky/cholinv.cpp protocol); reference validator residual {d['residual']:.2e}")
+    cfg = workload_config(ranks if ranks == 8 else 1, n, 2 if ranks == 8 else 1, bcm)
+    cfg["workload"] = "REFERENCE CPU SAMPLE: " + cfg["workload"]
+    cfg["full_workload_n"] = n_full
+    cfg["sample_n"] = n
     out = {
-        "impl": "reference", "metric": "cholesky_tflops_fp64", "value": val, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": 1, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": workload_config(args.gpus, n_full, c, bcm),
+        "impl": "reference", "metric": "cholesky_tflops_fp64", "value": val, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": iters,
+        "steps_requested": args.steps, "warmup": 1, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": d["cores"], "kind": "reference", "sample": sample},
         "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.time() - t0,
@@ -122,7 +136,101 @@ def workload_config(n_gpus, n, c, bcm):
             "n": n, "grid": f"{c}x{d}x{d}", "base_case": bc, "l2": "inputs larger than L2 (no flush needed)"}
 
 
+def parity_block(cb, torch, np, world, rank, c):
+    """Distributed results before anything is timed: the reference's own per-rank dumps (8 ranks) and the single-GPU factorization
+    of the same matrix (the generator is grid-independent).  Returns (max relative error, case list); all-reduced by the caller."""
+    gold = os.path.join(ROOT, "tests", "golden")
+    worst, cases = 0.0, []
+
+    def load(name):
+        z = np.load(os.path.join(gold, name + ".npz"))
+        return json.loads(str(z["meta"])), z
+
+    topo = cb.topo.square(world, rank, c)
+    d = topo.d
+    if world == 8:
+        for name in ("cholinv_p8_n128_ci0", "cholinv_p8_n192_ci1"):
+            meta, z = load(name)
+            n = meta["n"]
+            A = cb.matrix(n, n, 2, 2).distribute_symmetric(topo)
+            a = cb.cholinv.info(meta["complete_inv"], meta["split"], meta["bc_mult_dim"], "U")
+            cb.cholinv.factor(A, a, topo)
+            e = max(np.abs(a.R.cpu().numpy() - z[f"R_{rank}"]).max() / np.abs(z[f"R_{rank}"]).max(),
+                    np.abs(a.Rinv.cpu().numpy() - z[f"Rinv_{rank}"]).max() / np.abs(z[f"Rinv_{rank}"]).max())
+            if not np.array_equal(a.Rinv.cpu().numpy() == 0, z[f"Rinv_{rank}"] == 0):
+                e = 1.0
+            worst = max(worst, float(e)); cases.append(name)
+        t3 = cb.topo.rect(8, rank, 2)
+        meta, z = load("cacqr_p8_3d_m256_n64")
+        A = cb.matrix(meta["n"], meta["m"], 2, 2).distribute_random(t3, rank // 2)
+        qa = cb.cacqr.info(2, cb.cholinv.info(1, 1, -1, "U"))
+        cb.cacqr.factor(A, qa, t3)
+        worst = max(worst, float(np.abs(qa.Q.cpu().numpy() - z[f"Q_{rank}"]).max())); cases.append("cacqr_p8_3d_m256_n64")
+        qt = cb.topo.rect(8, rank, 1)
+        meta, z = load("cacqr_p8_1d_m1024_n32")
+        A = cb.matrix(meta["n"], meta["m"], 1, 8).distribute_random(qt, rank)
+        qa = cb.cacqr.info(2, cb.cholinv.info(0, 1, 0, "U"))
+        cb.cacqr.factor(A, qa, qt)
+        e = max(np.abs(qa.R.cpu().numpy() - z[f"R_{rank}"]).max() / np.abs(z[f"R_{rank}"]).max(), np.abs(qa.Q.cpu().numpy() - z[f"Q_{rank}"]).max())
+        worst = max(worst, float(e)); cases.append("cacqr_p8_1d_m1024_n32")
+    # distributed vs single GPU, a size with several distributed levels and 128-wide tiles
+    n = 4096 if world < 8 else 8192
+    bcm = -3
+    A = cb.matrix(n, n, d, d).distribute_symmetric(topo)
+    a = cb.cholinv.info(0, 1, bcm, "U")
+    cb.cholinv.factor(A, a, topo)
+    t1 = cb.topo.square(1, 0, 1)
+    A1 = cb.matrix(n, n, 1, 1).distribute_symmetric(t1)
+    a1 = cb.cholinv.info(0, 1, bcm, "U", serialize=False)
+    cb.cholinv.factor(A1, a1, t1)
+    R1, Ri1 = cb.cholinv.construct_R(a1), cb.cholinv.construct_Rinv(a1)
+    R, Ri = cb.cholinv.construct_R(a), cb.cholinv.construct_Rinv(a)
+    sel = (slice(topo.y, None, d), slice(topo.x, None, d))
+    e = max(((R - torch.triu(R1[sel])).abs().max() / R1.abs().max()).item(), ((Ri - torch.triu(Ri1[sel])).abs().max() / Ri1.abs().max()).item())
+    worst = max(worst, float(e)); cases.append(f"cholinv n={n} on {world} GPUs vs 1 GPU (elementwise R, Rinv)")
+    t1.context().release_workspace()
+    del A, a, A1, a1, R1, Ri1, R, Ri
+    torch.cuda.empty_cache()
+    return worst, cases
+
+
+def cacqr_record(cb, torch, dist, world, rank, peak_tf, hbm_gbs, steps):
+    """CholeskyQR2 (BASELINE config 4 at N = 8): m = 2^17 rows per GPU, n = 256, 1D row-partitioned grid, num_iter = 2."""
+    m, n = (1 << 17) * world, 256
+    qt = cb.topo.rect(world, rank, 1)
+    A = cb.matrix(n, m, 1, world).distribute_random(qt, rank)
+    qa = cb.cacqr.info(2, cb.cholinv.info(0, 1, 0, "U"))
+    for _ in range(3):
+        cb.cacqr.factor(A, qa, qt)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        cb.cacqr.factor(A, qa, qt)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item() / steps
+    res, orth = cb.cacqr.validate(A, qa, qt)
+    flops = 4.0 * m * n * n + 5.0 * n ** 3 / 3
+    tf = flops / (ms * 1e-3) / 1e12
+    bytes_alg = 2 * 3 * 8.0 * (m // world) * n  # per GPU: 2 sweeps x (2 reads + 1 write) of the local panel (SURVEY 8d)
+    rec = {"workload": f"cacqr::factor (CholeskyQR2) m={m} n={n} 1D grid 1x{world}, num_iter=2", "ms": ms, "tflops": tf,
+           "tflops_per_gpu": tf / world, "frac_of_dmma_peak": tf / world / peak_tf if peak_tf else None,
+           "hbm_gbs_per_gpu_algorithmic": bytes_alg / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": bytes_alg / (ms * 1e-3) / 1e9 / hbm_gbs,
+           "residual": res, "orthogonality": orth, "steps": steps}
+    qt.context().release_workspace()
+    return rec
+
+
 def ours(args):
+    import numpy as np
     import torch
     import torch.distributed as dist
     import capital_b200 as cb
@@ -147,18 +255,46 @@ def ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def reduce_max(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    # ---- parity of the distributed path, before anything is timed ----
+    parity = None
+    if world > 1 and not args.no_parity:
+        try:
+            worst, cases = parity_block(cb, torch, np, world, rank, c)
+            worst = reduce_max(worst)
+            parity = {"max_rel_err": worst, "cases": cases, "ok": bool(worst < 2e-13),
+                      "against": "tests/golden/*_p8_* (per-rank dumps of the reference run by oracle/_ref) and the single-GPU factorization"}
+        except Exception as ex:  # noqa
+            parity = {"max_rel_err": None, "ok": False, "error": repr(ex)[:300]}
+
     A = cb.matrix(n, n, dgrid, dgrid).distribute_symmetric(topo)
     pack = cb.cholinv.info(0, 1, bcm, "U")
     for _ in range(args.warmup):
         cb.cholinv.factor(A, pack, topo)
-    # ---- timed region: resident inputs ----
+    # ---- FP64 tensor-pipe peak of this device, now, with the clocks watched ----
     samples, stop = [], threading.Event()
     th = threading.Thread(target=clocks_sampler, args=(stop, samples, local_rank), daemon=True)
     barrier()
     if rank == 0:
         th.start()
+    try:
+        peak_tf, peak_ms = ctx.probe_dmma()
+        peak_src = f"DMMA.8x8x4 register loop on all SMs, {peak_ms:.1f} ms, CUDA events, measured in this run right before the timed steps (capital_probe_dmma_f64)"
+    except Exception as ex:  # noqa
+        peak_tf, peak_src = NOMINAL_DMMA_TFLOPS, f"NOMINAL 148 SM x 64 FMA/clk x 1.965 GHz (in-run probe failed: {ex!r})"
+    hbm_gbs = HBM_GBS_FALLBACK
+    try:
+        hbm_gbs = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    # ---- timed region: resident inputs ----
     ctx.reset_counters()
-    ctx.profile_begin()  # events around the dominant kernel's launches only (26 per step): negligible perturbation
+    ctx.profile_begin()  # events around the dominant kernel's launches only: negligible perturbation
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -173,6 +309,7 @@ def ours(args):
     # The timed steps overlap kernels on two streams, which stretches event-bracketed launch durations.  The roofline
     # number is therefore taken from one extra step with the deferred stream disabled (same kernels, same launches).
     ctx.set_overlap(False)
+    cb.cholinv.factor(A, pack, topo)
     ctx.profile_begin()
     barrier()
     e0.record()
@@ -182,10 +319,7 @@ def ours(args):
     s_ms_step = e0.elapsed_time(e1)
     s_ms, s_flops, s_launches = ctx.profile_end()
     ctx.set_overlap(True)
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = t.item() / args.steps
+    ms_step = reduce_max(ms) / args.steps
     value = n ** 3 / 3 / (ms_step * 1e-3) / 1e12
     residual = cb.cholinv.residual(A, pack, topo)
 
@@ -203,40 +337,79 @@ def ours(args):
             cb.cholinv.factor(hostA, hpack, topo)
         e1.record()
         barrier()
-        te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
         c2 = ctx.counters()
-        ms_e = te.item() / steps_e
+        ms_e = reduce_max(e0.elapsed_time(e1)) / steps_e
         e2e = {"value": n ** 3 / 3 / (ms_e * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": ms_e, "steps": steps_e,
                "h2d_bytes_per_step": c2.h2d_bytes // steps_e, "d2h_bytes_per_step": c2.d2h_bytes // steps_e,
                "note": "per rank; pinned host A in, pinned host R and Rinv (packed upper) out"}
         del hostA, hpack
     except Exception as ex:  # noqa
         e2e = {"value": None, "unit": "TFLOP/s", "error": repr(ex)[:200], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    del A, pack
+    torch.cuda.empty_cache()
+
+    # ---- fixed-size row: the same n on every N ----
+    strong = None
+    if not args.no_extra and not args.n:
+        try:
+            sb = STRONG_BCM[world]
+            As = cb.matrix(STRONG_N, STRONG_N, dgrid, dgrid).distribute_symmetric(topo)
+            sp = cb.cholinv.info(0, 1, sb, "U")
+            for _ in range(2):
+                cb.cholinv.factor(As, sp, topo)
+            barrier()
+            e0.record()
+            for _ in range(2):
+                cb.cholinv.factor(As, sp, topo)
+            e1.record()
+            barrier()
+            ms_s = reduce_max(e0.elapsed_time(e1)) / 2
+            strong = {"n": STRONG_N, "bc_mult_dim": sb, "ms_per_step": ms_s, "tflops": STRONG_N ** 3 / 3 / (ms_s * 1e-3) / 1e12,
+                      "residual": cb.cholinv.residual(As, sp, topo), "note": "same n at every N: strong scaling of cholinv::factor"}
+            del As, sp
+        except Exception as ex:  # noqa
+            strong = {"n": STRONG_N, "error": repr(ex)[:200]}
+        ctx.release_workspace()
+        torch.cuda.empty_cache()
+    # ---- CholeskyQR2 ----
+    cacqr = None
+    if not args.no_extra:
+        try:
+            cacqr = cacqr_record(cb, torch, dist, world, rank, peak_tf, hbm_gbs, max(3, args.steps))
+        except Exception as ex:  # noqa
+            cacqr = {"error": repr(ex)[:300]}
 
     if rank == 0:
         ach = s_flops / (s_ms * 1e-3) / 1e12 if s_ms > 0 else None
         ach_ov = k_flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else None
         out = {
             "metric": "cholesky_tflops_fp64", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "scaling_note": "sizes are BASELINE.json's per-N configs (n = 16384 / 24576 / 32768 / 65536: per-GPU work is NOT constant); "
+                            "`strong` repeats the measurement at one fixed n",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(world, n, c, bcm),
             "work_tflops": 5 * n ** 3 / 12 / (ms_step * 1e-3) / 1e12,  # CholInv with complete_inv=0 does 5n^3/12 flops
+            "work_frac_of_peak": 5 * n ** 3 / 12 / (ms_step * 1e-3) / 1e12 / (peak_tf * world),
             "residual": residual,
-            "roofline": {"bound": "tensor", "achieved": ach, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
-                         "frac": (ach / DMMA_PEAK_TFLOPS) if ach else None,
-                         # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the three launches captured with
-                         # `ncu --set full` (profiles/r01e_gemm_tn_ncu_full.md: 0.06 / 0.68 / 8.53 GB for the 2048 / 4096 / 8192 levels)
-                         "traffic": 3.09e9 if world == 1 else None,
-                         "kernel": "gemm_tn_kernel<128,128,64,32,5> (DMMA.8x8x4 + TMA)", "launches": s_launches,
+            "roofline": {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": (ach / peak_tf) if ach else None,
+                         "traffic": None,  # no `ncu --set full` capture of THIS build travels with the run; see profiles/ for the last one
+                         "kernel": "gemm_tn_kernel<128,128,64,32,5> (DMMA.8x8x4 + TMA" + (", depth exchange fused in the epilogue)" if world > 1 else ")"),
+                         "launches": s_launches,
                          "kernel_share_of_step": s_ms / s_ms_step if s_ms_step else None,
-                         "measured_in": "one extra step after the timed region with the deferred stream disabled (single-stream step "
-                                        f"{s_ms_step:.2f} ms); inside the overlapped timed region the same launches read {ach_ov:.2f} TF/s "
-                                        "because concurrent kernels share SMs" if ach_ov else None,
-                         "peak_source": "measured DMMA pipe peak on this pool (profiles/r01_fp64_pipe_ceilings.log); MEASURED_PEAKS.json has no FP64 entry"},
+                         "measured_in": (f"one extra step after the timed region with the deferred stream disabled (single-stream step {s_ms_step:.2f} ms); "
+                                         f"inside the overlapped timed region the same launches read {ach_ov:.2f} TF/s because concurrent kernels share SMs")
+                                        if ach_ov else None,
+                         "peak_source": peak_src},
             "e2e": e2e, "gpu_launches": int(cnt.kernel_launches), "clocks": summarize_clocks(samples),
         }
+        if parity is not None:
+            out["parity"] = parity
+        if strong is not None:
+            out["strong"] = strong
+        if cacqr is not None:
+            out["cacqr"] = cacqr
         if world == 1 and not args.no_cpu:
             d = run_reference_cholinv(min(n, 16384), bcm, 1, 1, timeout=600)
             if d and "time_mean_s" in d:
@@ -262,6 +435,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=0, help="override the matrix size (debug)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the N > 1 parity block")
+    ap.add_argument("--no-extra", action="store_true", help="skip the strong-scaling and CholeskyQR2 records")
     args = ap.parse_args()
     if args.gpus not in WORKLOADS:
         raise SystemExit("--gpus must be one of 1, 2, 4, 8")

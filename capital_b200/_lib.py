@@ -14,7 +14,7 @@ GEMM_A_UPPER, GEMM_A_LOWER, GEMM_B_UPPER, GEMM_B_LOWER, GEMM_C_UPPER = 1, 2, 4, 
 EXPORTS = [  # every symbol include/capital_b200.h declares
     "capital_grid_square", "capital_grid_rect", "capital_cholinv_bc_dimension", "capital_create",
     "capital_comm_unique_id", "capital_comm_init", "capital_comm_init_host", "capital_dist_trace_cholinv", "capital_destroy", "capital_last_error", "capital_get_counters",
-    "capital_reset_counters", "capital_synchronize", "capital_set_stream", "capital_release_workspace", "capital_last_factor_ms", "capital_profile_begin", "capital_profile_end", "capital_set_overlap", "capital_distribute_symmetric_f64",
+    "capital_reset_counters", "capital_synchronize", "capital_set_stream", "capital_release_workspace", "capital_last_factor_ms", "capital_profile_begin", "capital_profile_end", "capital_probe_dmma_f64", "capital_timeline_begin", "capital_timeline_end", "capital_set_overlap", "capital_distribute_symmetric_f64",
     "capital_distribute_random_f64", "capital_cholinv_factor_f64", "capital_cholinv_residual_f64",
     "capital_cacqr_factor_f64", "capital_cacqr_residual_f64", "capital_summa_gemm_tn_f64", "capital_blas_gemm_tn_f64",
     "capital_lapack_potrf_trtri_f64",
@@ -76,6 +76,9 @@ def lib() -> C.CDLL:
     L.capital_profile_begin.argtypes = [vp]
     L.capital_set_overlap.argtypes = [vp, ci]
     L.capital_profile_end.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(i64)]
+    L.capital_probe_dmma_f64.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl)]
+    L.capital_timeline_begin.argtypes = [vp]
+    L.capital_timeline_end.argtypes = [vp, C.POINTER(dbl), i64, C.POINTER(i64)]
     L.capital_distribute_symmetric_f64.argtypes = [vp, vp, i64, ci]
     L.capital_distribute_random_f64.argtypes = [vp, vp, i64, i64, i64]
     L.capital_cholinv_factor_f64.argtypes = [vp, vp, i64, C.POINTER(CholinvArgs), ci, vp, vp]
@@ -145,6 +148,24 @@ class Context:
         ms, fl, n = C.c_double(), C.c_double(), C.c_int64()
         self.check(lib().capital_profile_end(self._h, C.byref(ms), C.byref(fl), C.byref(n)))
         return float(ms.value), float(fl.value), int(n.value)
+
+    def timeline_begin(self):
+        self.check(lib().capital_timeline_begin(self._h))
+
+    def timeline_end(self):
+        """numpy array (launches x 8): stream id, kind, start ms, end ms, a, b, c, 0 -- see capital_timeline_end in the header."""
+        import numpy as np
+        n = C.c_int64()
+        cap = 1 << 18
+        buf = np.zeros((cap, 8), dtype=np.float64)
+        self.check(lib().capital_timeline_end(self._h, buf.ctypes.data_as(C.POINTER(C.c_double)), cap, C.byref(n)))
+        return buf[:min(cap, n.value)].copy()
+
+    def probe_dmma(self):
+        """(TFLOP/s, ms) of a register-resident DMMA.8x8x4 loop on every SM: the FP64 tensor-pipe ceiling of this device now."""
+        tf, ms = C.c_double(), C.c_double()
+        self.check(lib().capital_probe_dmma_f64(self._h, C.byref(tf), C.byref(ms)))
+        return float(tf.value), float(ms.value)
 
     def close(self):
         if self._h:

@@ -3,6 +3,7 @@
 // leaf.cu and layout.cu.  There is no CPU fallback: without a usable sm_100 device capital_create fails.
 #include "common.cuh"
 #include "dist.cuh"
+#include "peer.cuh"
 #include <math.h>
 #include <stdlib.h>
 
@@ -17,6 +18,34 @@ capital_status_t capital_ctx::workspace(const std::string& name, size_t bytes, v
   }
   *out = b.p;
   return CAPITAL_OK;
+}
+
+int capital_ctx::stream_id(cudaStream_t st) const {
+  if (st == hi) return 1;
+  if (st == side) return 2;
+  if (peer) {
+    const Peer* P = (const Peer*)peer;
+    for (int q = 0; q < PEER_Q; q++) if (st == P->push[q]) return 3 + q;
+  }
+  if (st == copy_in) return 6;
+  if (st == copy_out) return 7;
+  return 0;
+}
+int capital_ctx::tl_begin(cudaStream_t st, int kind, double a, double b, double c) {
+  if (!timeline) return -1;
+  while (tl_pool.size() < tl_used + 2) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return -1;
+    tl_pool.push_back(e);
+  }
+  TlRec r{tl_pool[tl_used], tl_pool[tl_used + 1], stream_id(st), kind, a, b, c};
+  tl_used += 2;
+  cudaEventRecord(r.e0, st);
+  tl.push_back(r);
+  return (int)tl.size() - 1;
+}
+void capital_ctx::tl_end(cudaStream_t st, int idx) {
+  if (idx >= 0) cudaEventRecord(tl[idx].e1, st);
 }
 
 bool cap_is_device_ptr(const void* p) {
@@ -226,6 +255,51 @@ int64_t capital_cholinv_bc_dimension(int64_t local_dim, int c, int d, int64_t bc
   return (int64_t)d * (local_dim / bc);
 }
 
+// The deferred stream gets its own SM partition (a CUDA green context): all SMs but `reserve` of them.  Deferred GEMM tiles hold an
+// SM for up to ~1 ms and a running CTA cannot be preempted, so without a partition the latency-critical kernels of the chain
+// (8-CTA cluster base case, small products) wait that long for SMs although their stream has the higher priority: measured
+// 8034 us vs 144 us for ten 10-us cluster kernels behind a saturating low-priority kernel (profiles/r02a_probe_greenctx.log).
+// The chain's streams stay in the primary context and may use every SM.
+static bool make_green_side_stream(capital_ctx* ctx, int reserve, int prio) {
+  typedef CUresult (*fn_devget)(CUdevice*, int);
+  typedef CUresult (*fn_getres)(CUdevice, CUdevResource*, CUdevResourceType);
+  typedef CUresult (*fn_split)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int);
+  typedef CUresult (*fn_desc)(CUdevResourceDesc*, CUdevResource*, unsigned int);
+  typedef CUresult (*fn_gcreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int);
+  typedef CUresult (*fn_gstream)(CUstream*, CUgreenCtx, unsigned int, int);
+  void *p1 = nullptr, *p2 = nullptr, *p3 = nullptr, *p4 = nullptr, *p5 = nullptr, *p6 = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuDeviceGet", &p1, cudaEnableDefault, &q) != cudaSuccess || !p1) return false;
+  if (cudaGetDriverEntryPoint("cuDeviceGetDevResource", &p2, cudaEnableDefault, &q) != cudaSuccess || !p2) return false;
+  if (cudaGetDriverEntryPoint("cuDevSmResourceSplitByCount", &p3, cudaEnableDefault, &q) != cudaSuccess || !p3) return false;
+  if (cudaGetDriverEntryPoint("cuDevResourceGenerateDesc", &p4, cudaEnableDefault, &q) != cudaSuccess || !p4) return false;
+  if (cudaGetDriverEntryPoint("cuGreenCtxCreate", &p5, cudaEnableDefault, &q) != cudaSuccess || !p5) return false;
+  if (cudaGetDriverEntryPoint("cuGreenCtxStreamCreate", &p6, cudaEnableDefault, &q) != cudaSuccess || !p6) return false;
+  CUdevice dev;
+  if (((fn_devget)p1)(&dev, ctx->device) != CUDA_SUCCESS) return false;
+  CUdevResource all, rem;
+  if (((fn_getres)p2)(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return false;
+  unsigned nb = 0;
+  if (((fn_split)p3)(nullptr, &nb, &all, nullptr, 0, 8) != CUDA_SUCCESS || nb < 2) return false;
+  std::vector<CUdevResource> groups(nb);
+  if (((fn_split)p3)(groups.data(), &nb, &all, &rem, 0, 8) != CUDA_SUCCESS) return false;
+  unsigned skip = 0, got = 0;
+  while (skip < nb - 1 && (int)got < reserve) got += groups[skip++].sm.smCount;
+  std::vector<CUdevResource> far(groups.begin() + skip, groups.begin() + nb);
+  if (rem.sm.smCount) far.push_back(rem);
+  CUdevResourceDesc desc;
+  if (((fn_desc)p4)(&desc, far.data(), (unsigned)far.size()) != CUDA_SUCCESS) return false;
+  CUgreenCtx g;
+  if (((fn_gcreate)p5)(&g, desc, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
+  CUstream gs;
+  if (((fn_gstream)p6)(&gs, g, CU_STREAM_NON_BLOCKING, prio) != CUDA_SUCCESS) return false;
+  ctx->side = (cudaStream_t)gs;
+  ctx->green = (void*)g;
+  ctx->side_sms = 0;
+  for (auto& r : far) ctx->side_sms += (int)r.sm.smCount;
+  return true;
+}
+
 capital_status_t capital_create(capital_ctx** out, const capital_grid_t* grid, int device, void* stream) {
   if (!out || !grid) return CAPITAL_ERR_INVALID;
   *out = nullptr;
@@ -246,7 +320,11 @@ capital_status_t capital_create(capital_ctx** out, const capital_grid_t* grid, i
   }
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // lo = numerically greatest = lowest priority
-  bool ok = cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, prio_lo) == cudaSuccess;
+  int reserve = 8;  // SMs kept free of deferred work [env CAPITAL_GREEN_SMS; 0 = plain low-priority stream]
+  if (const char* e = getenv("CAPITAL_GREEN_SMS")) reserve = atoi(e);
+  bool ok = true;
+  if (reserve <= 0 || !make_green_side_stream(ctx, reserve, prio_lo))
+    ok = cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, prio_lo) == cudaSuccess;
   ok = ok && cudaStreamCreateWithPriority(&ctx->hi, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking) == cudaSuccess;
@@ -286,7 +364,14 @@ void capital_destroy(capital_ctx* ctx) {
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->tl_pool) cudaEventDestroy(e);
   if (ctx->side) cudaStreamDestroy(ctx->side);
+  if (ctx->green) {
+    typedef CUresult (*fn_gdestroy)(CUgreenCtx);
+    void* pd = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuGreenCtxDestroy", &pd, cudaEnableDefault, &q) == cudaSuccess && pd) ((fn_gdestroy)pd)((CUgreenCtx)ctx->green);
+  }
   if (ctx->hi) cudaStreamDestroy(ctx->hi);
   if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
   if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
@@ -342,6 +427,40 @@ capital_status_t capital_last_factor_ms(const capital_ctx* ctx_, float* ms) {
   return CAPITAL_OK;
 }
 
+capital_status_t capital_timeline_begin(capital_ctx* ctx) {
+  if (!ctx) return CAPITAL_ERR_INVALID;
+  ctx->timeline = true; ctx->tl.clear(); ctx->tl_used = 0;
+  return CAPITAL_OK;
+}
+capital_status_t capital_timeline_end(capital_ctx* ctx, double* out, int64_t cap_records, int64_t* n_records) {
+  if (!ctx || !n_records) return CAPITAL_ERR_INVALID;
+  ctx->timeline = false;
+  CAP_CUDA(cudaSetDevice(ctx->device));
+  CAP_CUDA(cudaDeviceSynchronize());
+  *n_records = (int64_t)ctx->tl.size();
+  if (out && !ctx->tl.empty()) {
+    // time origin: the earliest start
+    cudaEvent_t base = ctx->tl[0].e0;
+    for (auto& r : ctx->tl) {
+      float d = 0;
+      if (cudaEventElapsedTime(&d, base, r.e0) == cudaSuccess && d < 0) base = r.e0;
+    }
+    for (int64_t i = 0; i < *n_records && i < cap_records; i++) {
+      const auto& r = ctx->tl[i];
+      float t0 = 0, t1 = 0;
+      CAP_CUDA(cudaEventElapsedTime(&t0, base, r.e0));
+      CAP_CUDA(cudaEventElapsedTime(&t1, base, r.e1));
+      double* o = out + i * 8;
+      o[0] = r.sid; o[1] = r.kind; o[2] = t0; o[3] = t1; o[4] = r.a; o[5] = r.b; o[6] = r.c; o[7] = 0;
+    }
+  }
+  return CAPITAL_OK;
+}
+capital_status_t capital_probe_dmma_f64(capital_ctx* ctx, double* tflops, double* ms) {
+  if (!ctx || !tflops || !ms) return CAPITAL_ERR_INVALID;
+  CAP_CUDA(cudaSetDevice(ctx->device));
+  return gemm_probe_dmma(ctx, tflops, ms);
+}
 capital_status_t capital_set_overlap(capital_ctx* ctx, int enabled) {
   if (!ctx) return CAPITAL_ERR_INVALID;
   ctx->no_overlap = !enabled;

@@ -41,7 +41,9 @@ struct capital_ctx {
   int device = 0;
   int num_sms = 148;
   cudaStream_t stream = nullptr;   // main stream (caller's or owned)
-  cudaStream_t side = nullptr;     // low-priority stream: deferred ("far") trailing updates, T^T products
+  cudaStream_t side = nullptr;     // low-priority stream: deferred ("far") trailing updates, T^T products; lives in a green context
+  void* green = nullptr;           // (CUgreenCtx) SM partition of the deferred stream, see make_green_side_stream (api.cu)
+  int side_sms = 0;                // SMs of that partition (0: no partition)
   cudaStream_t hi = nullptr;       // high-priority stream: the critical chain of the recursion
   cudaStream_t copy_in = nullptr, copy_out = nullptr;  // H2D / D2H streams of the host-pointer path
   // EXPERIMENTAL, off by default [env CAPITAL_ZC_OUT=1]: host outputs leave block by block through a kernel that stores straight
@@ -90,6 +92,16 @@ struct capital_ctx {
     return CAPITAL_OK;
   }
 
+  // timeline (debug / profiling): CUDA events around every launch of the schedule, read back by capital_timeline_end
+  struct TlRec { cudaEvent_t e0, e1; int sid, kind; double a, b, c; };
+  bool timeline = false;
+  std::vector<TlRec> tl;
+  std::vector<cudaEvent_t> tl_pool;
+  size_t tl_used = 0;
+  int stream_id(cudaStream_t st) const;  // 0 caller, 1 chain, 2 deferred, 3.. push streams, 6 copy-in, 7 copy-out
+  int tl_begin(cudaStream_t st, int kind, double a = 0, double b = 0, double c = 0);
+  void tl_end(cudaStream_t st, int idx);
+
   void set_error(const std::string& s) { err = s; }
   capital_status_t workspace(const std::string& name, size_t bytes, void** out);
   capital_status_t pinned_buf(size_t bytes, void** out);
@@ -98,6 +110,7 @@ struct capital_ctx {
 // ---- gemm_tn.cu -------------------------------------------------------------------------------
 capital_status_t gemm_tn_init(capital_ctx* ctx);  // per-device kernel attributes
 capital_status_t leaf_init(capital_ctx* ctx);
+capital_status_t gemm_probe_dmma(capital_ctx* ctx, double* tflops, double* ms);
 
 // Multi-GPU form of the product (dist.cu).  (1) The contraction may run over several operand CLASSES -- the k-slices owned by
 // different process rows (summa.hpp:185-193), fetched into local mirrors -- inside one launch, accumulators staying in

@@ -223,8 +223,10 @@ struct Dist {
       rec(T_DMA, sid, dst_rank);
       return CAPITAL_OK;
     }
+    const int tli = ctx->tl_begin(strm(sid), 7, (double)rows, (double)cols, (double)dst_rank);
     if (rows == lds && rows == ldd) CAP_CUDA(cudaMemcpyAsync(dst, src, (size_t)rows * cols * 8, cudaMemcpyDefault, strm(sid)));
     else CAP_CUDA(cudaMemcpy2DAsync(dst, (size_t)ldd * 8, src, (size_t)lds * 8, (size_t)rows * 8, (size_t)cols, cudaMemcpyDefault, strm(sid)));
+    ctx->tl_end(strm(sid), tli);
     return CAPITAL_OK;
   }
 };

@@ -396,6 +396,41 @@ capital_status_t launch(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n,
 
 }  // namespace
 
+// ---- FP64 tensor-pipe ceiling, measured in place ------------------------------------------------------------------
+// Register-resident DMMA.8x8x4 loop (8 independent accumulator pairs per warp, 8 warps per SM): what the tensor pipe delivers with
+// no memory traffic at all.  bench.py runs it next to the timed steps so that `roofline.peak` is a number of THIS device at THIS
+// clock, not a constant from a file.
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters, double s) {
+  double c[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { c[i][0] = 0.0; c[i][1] = 0.0; }
+  const double a = s + threadIdx.x * 1e-6, b = 1.0 - s;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+  }
+  double r = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r += c[i][0] + c[i][1];
+  if (r == 123.456) out[0] = r;
+}
+capital_status_t gemm_probe_dmma(capital_ctx* ctx, double* tflops, double* ms_out) {
+  const int iters = 100000, blocks = ctx->num_sms;
+  cudaStream_t st = ctx->stream;
+  dmma_peak_kernel<<<blocks, 256, 0, st>>>(ctx->d_scalars + 8, iters / 10, 0.5);  // warm-up
+  CAP_CUDA(cudaEventRecord(ctx->ev_start, st));
+  dmma_peak_kernel<<<blocks, 256, 0, st>>>(ctx->d_scalars + 8, iters, 0.5);
+  CAP_CUDA(cudaEventRecord(ctx->ev_stop, st));
+  CAP_CUDA(cudaStreamSynchronize(st));
+  float ms = 0;
+  CAP_CUDA(cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop));
+  const double flops = 2.0 * 256.0 * 8.0 * (double)iters * 8.0 * (double)blocks;  // 8x8x4 MACs x 8 accumulators x 8 warps x blocks
+  *tflops = flops / (ms * 1e-3) / 1e12;
+  *ms_out = ms;
+  return CAPITAL_OK;
+}
+
 // Per-device kernel attributes (the >48 KB dynamic shared memory opt-in is a per-device property): called from capital_create
 // after cudaSetDevice, so that every context's device is prepared whatever the process did before.
 capital_status_t gemm_tn_init(capital_ctx* ctx) {
@@ -496,12 +531,17 @@ capital_status_t gemm_tn_x(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t
       CAP_TRY(ctx->prof_event(&e0)); CAP_TRY(ctx->prof_event(&e1));
       CAP_CUDA(cudaEventRecord(e0, st));
     }
+    const int tli = ctx->tl_begin(st, 1, (double)m, (double)n, (double)k * ops.ncls);
     CAP_TRY((launch<CfgBig>(ctx, st, m, n, k, alpha, ops, beta, C, ldc, flags, 1, koff, noff, x)));
+    ctx->tl_end(st, tli);
     if (ctx->profiling) {
       CAP_CUDA(cudaEventRecord(e1, st));
       ctx->prof_recs.push_back({e0, e1, f});
     }
     return CAPITAL_OK;
   }
-  return launch<CfgSmall>(ctx, st, m, n, k, alpha, ops, beta, C, ldc, flags, 1, koff, noff, x);
+  const int tli = ctx->tl_begin(st, 2, (double)m, (double)n, (double)k * ops.ncls);
+  const capital_status_t rs = launch<CfgSmall>(ctx, st, m, n, k, alpha, ops, beta, C, ldc, flags, 1, koff, noff, x);
+  ctx->tl_end(st, tli);
+  return rs;
 }

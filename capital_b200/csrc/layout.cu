@@ -188,7 +188,9 @@ capital_status_t transpose_block(capital_ctx* ctx, cudaStream_t st, int64_t rows
                                  double* dst, int64_t ldd, double scale) {
   if (rows <= 0 || cols <= 0) return CAPITAL_OK;
   dim3 grid((unsigned)ceil_div(rows, TP), (unsigned)ceil_div(cols, TP)), block(TP, 8);
+  const int tli = ctx->tl_begin(st, 8, 1, (double)rows, (double)cols);
   transpose_kernel<<<grid, block, 0, st>>>((int)rows, (int)cols, src, lds, dst, ldd, scale);
+  ctx->tl_end(st, tli);
   LAUNCH_CHECK();
   return CAPITAL_OK;
 }
@@ -199,7 +201,9 @@ capital_status_t copy_block(capital_ctx* ctx, cudaStream_t st, int64_t rows, int
     CAP_CUDA(cudaMemcpyAsync(dst, src, (size_t)rows * cols * 8, cudaMemcpyDeviceToDevice, st));
     return CAPITAL_OK;
   }
+  const int tli = ctx->tl_begin(st, 8, 2, (double)rows, (double)cols);
   copy_kernel<<<grid_for(ctx, rows * cols, 256), 256, 0, st>>>(rows, cols, src, lds, dst, ldd);
+  ctx->tl_end(st, tli);
   LAUNCH_CHECK();
   return CAPITAL_OK;
 }
@@ -218,7 +222,9 @@ capital_status_t pack_upper(capital_ctx* ctx, cudaStream_t st, int64_t n, const 
   if (col_end < 0) col_end = n;
   const int64_t cols = col_end - col_begin;
   if (cols <= 0) return CAPITAL_OK;
+  const int tli = ctx->tl_begin(st, 8, 3, (double)col_begin, (double)col_end);
   pack_upper_kernel<<<(int)(cols < ctx->num_sms * 8 ? cols : ctx->num_sms * 8), 256, 0, st>>>(col_begin, col_end, src, lds, packed, zero_diag);
+  ctx->tl_end(st, tli);
   LAUNCH_CHECK();
   return CAPITAL_OK;
 }

@@ -627,7 +627,9 @@ capital_status_t leaf_cholinv(capital_ctx* ctx, cudaStream_t st, int nb, const d
   if (nb <= 0) return CAPITAL_OK;
   if (nb > LEAF_MAX) return CAPITAL_ERR_INVALID;
   constexpr int smem = LEAF_SMEM;
+  const int tli = ctx->tl_begin(st, 4, nb);
   leaf_kernel<<<1, 256, smem, st>>>(nb, W, ldw, R, ldr, Ri, ldri, RiT, ldrit, ctx->d_info);
+  ctx->tl_end(st, tli);
   ctx->counters.kernel_launches++;
   ctx->counters.leaf_launches++;
   CAP_CUDA(cudaGetLastError());
@@ -644,7 +646,9 @@ capital_status_t basecase_cholinv(capital_ctx* ctx, cudaStream_t st, int nb, dou
     CAP_TRY(ctx->workspace("bc_dbg", 64 * sizeof(long long), (void**)&dbg));
     CAP_CUDA(cudaMemsetAsync(dbg, 0, 64 * sizeof(long long), st));
   }
+  const int tli = ctx->tl_begin(st, 3, nb);
   basecase_kernel<<<BC_CLUSTER, 256, smem, st>>>(nb, W, ldw, R, ldr, Ri, ldri, RiT, ldrit, ctx->d_info, dbg);
+  ctx->tl_end(st, tli);
   if (dbg) {
     long long h[32];
     CAP_CUDA(cudaMemcpyAsync(h, dbg, sizeof(h), cudaMemcpyDeviceToHost, st));

@@ -200,14 +200,18 @@ capital_status_t peer_arena_reserve(capital_ctx* ctx, size_t bytes) {
 
 capital_status_t peer_signal(capital_ctx* ctx, cudaStream_t st, const FlagList& fl) {
   if (fl.n == 0) return CAPITAL_OK;
+  const int tli = ctx->tl_begin(st, 6, fl.n);
   signal_kernel<<<1, 32, 0, st>>>(fl);
+  ctx->tl_end(st, tli);
   ctx->counters.kernel_launches++;
   CAP_CUDA(cudaGetLastError());
   return CAPITAL_OK;
 }
 capital_status_t peer_wait(capital_ctx* ctx, cudaStream_t st, const FlagList& fl) {
   if (fl.n == 0) return CAPITAL_OK;
+  const int tli = ctx->tl_begin(st, 5, fl.n);
   wait_kernel<<<1, 32, 0, st>>>(fl, ctx->d_info);
+  ctx->tl_end(st, tli);
   ctx->counters.kernel_launches++;
   CAP_CUDA(cudaGetLastError());
   return CAPITAL_OK;
