@@ -113,27 +113,20 @@ capital_status_t leaf_init(capital_ctx* ctx);
 capital_status_t gemm_probe_dmma(capital_ctx* ctx, double* tflops, double* ms);
 
 // Multi-GPU form of the product (dist.cu).  (1) The contraction may run over several operand CLASSES -- the k-slices owned by
-// different process rows (summa.hpp:185-193), fetched into local mirrors -- inside one launch, accumulators staying in
-// registers.  (2) The depth reduction of the reference (MPI_Allreduce over the c layers, summa.hpp:236) is fused into the
-// epilogue over peer-mapped memory:
-//   mode 1 (k split over layers, c == d): every layer computes a partial of every tile; tile (tm, tn) is OWNED by layer
-//          (tm + tn) mod c.  Non-owners store their partial (in register-fragment order, 16-byte coalesced) straight into the
-//          owner's receive buffer over NVLink and raise a per-tile flag; the owner adds the partials to its accumulators,
-//          applies alpha / beta and stores the FINAL tile into the C replica of every layer.  Tiles are handed out by a ticket
-//          counter, all non-owned tiles before any owned one, so a waiting owner only ever waits for tiles that never wait.
-//   mode 2 (n split, d == 1): layer tn mod c computes tile column tn with the full k range and stores it to every replica.
+// different process rows (summa.hpp:185-193), resident in local mirrors -- inside one launch, accumulators staying in
+// registers.  (2) The first half of the reference's depth reduction (MPI_Allreduce over the c layers, summa.hpp:236) is fused
+// into the epilogue over peer-mapped memory: every stored value also goes, over NVLink, into buffers of the other layers.
+//   mode 1 (k split over layers, c == d): C is this layer's PARTIAL-product buffer and Cpeer[i] the receive buffer that the i-th
+//          other layer keeps for this layer: when the kernel has retired on every layer (one flag handshake), each layer holds all
+//          c partials and adds them up in layer order with one streaming pass (dist.cu: reduce_partials) -- identical bits in
+//          every replica, no collective call, no in-kernel waiting.
+//   mode 2 (n split, d == 1): layer tn mod c computes tile column tn with the full k range and stores the FINAL values into its own
+//          C and into the C replica of every other layer (Cpeer[i]).
 constexpr int GEMM_NCLS_MAX = 2;
 constexpr int GEMM_XPEERS_MAX = 3;
 struct GemmXDev {
   int mode, c, z;
-  unsigned long long seq;                               // flag value of this product (monotonic over the context's lifetime)
-  unsigned int* ticket;                                 // zero on entry
-  double* Cpeer[GEMM_XPEERS_MAX];                       // C window inside the replica of the i-th OTHER layer
-  double* precv_local[GEMM_XPEERS_MAX];                 // my receive buffer for the i-th other layer's partials
-  double* precv_peer[GEMM_XPEERS_MAX];                  // the i-th other layer's receive buffer for MY partials
-  unsigned long long* tflag_local[GEMM_XPEERS_MAX];     // per-tile arrival flags, same indexing
-  unsigned long long* tflag_peer[GEMM_XPEERS_MAX];
-  int* err;                                             // set to -1 when a wait times out
+  double* Cpeer[GEMM_XPEERS_MAX];  // same window as C inside the i-th OTHER layer's buffer
 };
 struct GemmOperands {
   int ncls = 1;
@@ -141,8 +134,6 @@ struct GemmOperands {
   const double* B[GEMM_NCLS_MAX] = {nullptr, nullptr};
   int64_t lda = 0, ldb = 0;
 };
-// bytes of receive buffer / number of tile flags a mode-1 product of this shape needs (per other layer)
-void gemm_tn_xsizes(const capital_ctx* ctx, int64_t m, int64_t n, size_t* precv_bytes, size_t* tiles);
 capital_status_t gemm_tn_x(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const GemmOperands& ops,
                            double beta, double* C, int64_t ldc, int flags, int koff, int noff, const GemmXDev* x);
 capital_status_t gemm_tn(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const double* A,

@@ -66,6 +66,36 @@ __global__ void dense_to_local3_kernel(int s, int d, int x, int y, const double*
   }
 }
 
+// Second half of the depth reduction (summa.hpp:236): C = beta * C + sum over the layers' partial products, added in LAYER ORDER on
+// every layer (identical bits in every replica).  One streaming pass: every partial is read once, C is read (beta != 0) and written
+// once.  upper_only: entries with row > col0 + col are left alone (the producing GEMM only computed the upper tiles).
+struct PartialSrc { const double* p[GEMM_XPEERS_MAX + 1]; int n; };
+__global__ void __launch_bounds__(256) reduce_partials_kernel(long long rows, long long cols, PartialSrc src, long long ldp, double beta,
+                                                              double* __restrict__ C, long long ldc, int upper_only, long long col0) {
+  const long long r2 = (rows + 1) / 2;  // row pairs: every buffer is 16-byte aligned with an even leading dimension
+  for (long long c = blockIdx.y; c < cols; c += gridDim.y) {
+    const long long rmax = upper_only ? min(rows, c + col0 + 1) : rows;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < r2; i += (long long)gridDim.x * blockDim.x) {
+      const long long r = 2 * i;
+      if (r >= rmax) break;
+      double2 v = __ldcs(reinterpret_cast<const double2*>(src.p[0] + c * ldp + r));
+      for (int l = 1; l < src.n; l++) {
+        const double2 w = __ldcs(reinterpret_cast<const double2*>(src.p[l] + c * ldp + r));
+        v.x += w.x; v.y += w.y;
+      }
+      double* cc = C + c * ldc + r;
+      if (r + 1 < rmax && ((ldc | (long long)(((uintptr_t)C) >> 3)) & 1) == 0) {
+        double2* c2 = reinterpret_cast<double2*>(cc);
+        if (beta != 0.0) { const double2 o = *c2; v.x += beta * o.x; v.y += beta * o.y; }
+        *c2 = v;
+      } else {
+        cc[0] = beta != 0.0 ? beta * cc[0] + v.x : v.x;
+        if (r + 1 < rmax) cc[1] = beta != 0.0 ? beta * cc[1] + v.y : v.y;
+      }
+    }
+  }
+}
+
 inline int grid_for(const capital_ctx* ctx, long long total) {
   long long b = (total + 255) / 256;
   const long long cap = (long long)ctx->num_sms * 8;
@@ -128,14 +158,19 @@ struct Dist {
   int64_t L = 0, ld = 0, bc_local = 0;
   int split = 1;
   DMat W, R, Ri, RiT;
-  double* precv[PEER_QC] = {nullptr, nullptr};
-  size_t precv_stride = 0;  // doubles between the receive buffers of two layers
+  // partial products of the k-split exchange, per stream class: my own partial, and two alternating sets of receive buffers (one
+  // per other layer) that the partners' GEMM epilogues store into
+  double* pown[PEER_QC] = {nullptr, nullptr};
+  double* precv[PEER_QC][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  size_t precv_stride = 0;  // doubles per partial buffer
   double* gath[2] = {nullptr, nullptr};
   int64_t gath_blk = 0;
   unsigned long long bc_count = 0;
   double *bcW = nullptr, *bcR = nullptr, *bcRi = nullptr, *bcRiT = nullptr;
   bool two_stream = true;
   int64_t far_min = 1024, side_min = 512;
+  int64_t chunk_min = 4096;  // R12 / Rinv12 blocks at least this wide are produced and pushed in `chunks` column chunks [env CAPITAL_DIST_CHUNK_MIN]
+  int chunks = 4;            // [env CAPITAL_DIST_CHUNKS]
   // host-pointer callers: A arrives by column chunks on the copy-in stream; finished column ranges are packed and copied out while
   // the rest of the factorization runs
   std::vector<std::pair<int64_t, int>> in_chunks;  // (col_end, event)
@@ -296,6 +331,8 @@ capital_status_t dist_setup(Dist& D, capital_ctx* ctx, bool dry) {
   if (const char* e = getenv("CAPITAL_DIST_TWO_STREAM")) D.two_stream = atoi(e) != 0;
   if (const char* e = getenv("CAPITAL_DIST_FAR_MIN")) D.far_min = atoll(e);
   if (const char* e = getenv("CAPITAL_DIST_SIDE_MIN")) D.side_min = atoll(e);
+  if (const char* e = getenv("CAPITAL_DIST_CHUNK_MIN")) D.chunk_min = atoll(e);
+  if (const char* e = getenv("CAPITAL_DIST_CHUNKS")) D.chunks = atoi(e);
   if (ctx->no_overlap) D.two_stream = false;
   return CAPITAL_OK;
 }
@@ -326,6 +363,17 @@ void layout_mat(Layout& lay, const Dist& D, DMat& M, int64_t ld, int64_t cols, i
     const double* slots[2 * NK_MAX + 2] = {M.own, M.xs[0], M.xs[1], M.ys[0], M.ys[1], M.ts};
     for (const double* p : slots)
       if (p) const_cast<Dist&>(D).rec(T_MAT, 0, (const char*)p - D.P->arena, ld, cols);
+  }
+}
+
+// partial-product buffers of the k-split exchange for products up to m x n, for the first `classes` stream classes
+void layout_exchange(Layout& lay, Dist& D, int64_t m, int64_t n, int classes) {
+  D.precv_stride = 0;
+  if (D.xmode != 1) return;
+  D.precv_stride = (size_t)round_up((int64_t)((size_t)packed_ld(m) * n), 128);
+  for (int q = 0; q < classes; q++) {
+    D.pown[q] = lay.take(D.precv_stride);
+    for (int b = 0; b < 2; b++) D.precv[q][b] = lay.take(D.precv_stride * (size_t)(D.c - 1));
   }
 }
 
@@ -376,7 +424,8 @@ inline void add_waits(const Dist& D, std::vector<Flag>& w, int s, const Token* t
 
 // One distributed product  C <- beta*C + alpha * X^T Y  on stream class q (all matrices are windows of cyclically distributed
 // globals; local windows: X: k x m, Y: k x n, C: m x n).  The blocks actually multiplied are the ones owned by the class sources;
-// the result is complete in EVERY replica when the call's work has drained from the class stream.
+// the result is complete in EVERY replica when the call's work has drained from the class stream.  `noff`: column position of the
+// window inside the full operand (column-chunked products keep the triangular k ranges and the upper mask right).
 capital_status_t product(Dist& D, int q, int64_t m, int64_t n, int64_t k, double alpha, Win X, Win Y, double beta, Win C, int flags,
                          const Token* farX = nullptr, const Token* farY = nullptr, int noff = 0) {
   capital_ctx* ctx = D.ctx;
@@ -398,35 +447,18 @@ capital_status_t product(Dist& D, int q, int64_t m, int64_t n, int64_t k, double
   }
   CAP_TRY(D.wait_flags(sid, w));
   double* Cown = C.M->own + C.r0 + C.c0 * C.M->ld;
-  GemmXDev x{};
-  unsigned long long seq = 0;
-  if (D.xmode) {
-    seq = ++P->prod_seq[q];
-    x.mode = D.xmode; x.c = D.c; x.z = D.g.z; x.seq = seq; x.ticket = D.dry ? nullptr : P->tickets + q; x.err = ctx->d_info;
-    size_t need = 0, tiles = 0;
-    gemm_tn_xsizes(ctx, m, n, &need, &tiles);
-    if (D.xmode == 1 && (tiles > (size_t)PEER_TILEFLAGS || need > D.precv_stride * 8)) {
-      ctx->set_error("distributed product: exchange buffers too small for a " + std::to_string(m) + " x " + std::to_string(n) + " product");
-      return CAPITAL_ERR_UNSUPPORTED;
-    }
-    for (int l = 0; l < D.c; l++) {
-      if (l == D.g.z) continue;
-      const int oi = l < D.g.z ? l : l - 1;            // index of layer l among MY others
-      const int mi = D.g.z < l ? D.g.z : D.g.z - 1;    // index of my layer among layer l's others
-      const int partner = rank_of(D.g, D.g.x, D.g.y, l);
-      x.Cpeer[oi] = peer_ptr(P, partner, Cown);
-      if (D.xmode == 1) {
-        x.precv_local[oi] = D.precv[q] + (size_t)oi * D.precv_stride;
-        x.precv_peer[oi] = peer_ptr(P, partner, D.precv[q] + (size_t)mi * D.precv_stride);
-        x.tflag_local[oi] = D.dry ? nullptr : P->ctrl + CTRL_TILE + ((size_t)q * GEMM_XPEERS_MAX + oi) * PEER_TILEFLAGS;
-        x.tflag_peer[oi] = D.dry ? nullptr : ctrl_ptr(P, partner, CTRL_TILE + ((size_t)q * GEMM_XPEERS_MAX + mi) * PEER_TILEFLAGS);
-      }
-    }
+  const int64_t ldc = C.M->ld;
+  if (D.xmode == 0) {
+    if (D.dry) {
+      for (int j = 0; j < D.nk; j++) { D.rd(sid, ops.A[j], ops.lda, k, m); D.rd(sid, ops.B[j], ops.ldb, k, n); }
+      D.wr(sid, D.me, Cown, ldc, m, n);
+      D.rec(T_PRODUCT, sid, q, 0, 0);
+    } else CAP_TRY(gemm_tn_x(ctx, D.strm(sid), m, n, k, alpha, ops, beta, Cown, ldc, flags, 0, noff, nullptr));
+    return CAPITAL_OK;
   }
   // Flags of the depth handshake: ready(p) = 2 seq - 1 ("nothing I enqueued before product p still reads its C window"), done(p) =
-  // 2 seq ("my kernel has retired: my partials / final tiles are stored").  With the n split a layer stores final tiles into its
-  // partners' C without needing anything from them, so it must first know they are ready; with the k split an owner cannot finish
-  // a tile before the partner's kernel has started, which is the same guarantee for free.
+  // 2 seq ("my kernel has retired: everything it stored, here and in the partners' memory, is performed").
+  const unsigned long long seq = ++P->prod_seq[q];
   auto handshake = [&](unsigned long long v) -> capital_status_t {
     std::vector<Flag> s, ww;
     for (int l = 0; l < D.c; l++) {
@@ -438,16 +470,79 @@ capital_status_t product(Dist& D, int q, int64_t m, int64_t n, int64_t k, double
     CAP_TRY(D.signal_flags(sid, s));
     return D.wait_flags(sid, ww);
   };
-  if (D.xmode == 2) CAP_TRY(handshake(2 * seq - 1));
+  GemmXDev x{};
+  x.mode = D.xmode; x.c = D.c; x.z = D.g.z;
+  if (D.xmode == 2) {
+    // n split (d == 1): a layer stores final tiles into its partners' C without needing anything from them, so it must first know
+    // that they are done reading it
+    for (int l = 0; l < D.c; l++) {
+      if (l == D.g.z) continue;
+      x.Cpeer[l < D.g.z ? l : l - 1] = peer_ptr(P, rank_of(D.g, D.g.x, D.g.y, l), Cown);
+    }
+    CAP_TRY(handshake(2 * seq - 1));
+    if (D.dry) {
+      D.rd(sid, ops.A[0], ops.lda, k, m); D.rd(sid, ops.B[0], ops.ldb, k, n);
+      const int64_t group = (int64_t)(seq * 4 + q + 1);
+      D.wr(sid, D.me, Cown, ldc, m, n, group);
+      for (int l = 0; l < D.c; l++)
+        if (l != D.g.z) D.wr(sid, rank_of(D.g, D.g.x, D.g.y, l), Cown, ldc, m, n, group);
+      D.rec(T_PRODUCT, sid, q, (int64_t)seq, 2);
+    } else CAP_TRY(gemm_tn_x(ctx, D.strm(sid), m, n, k, alpha, ops, beta, Cown, ldc, flags, 0, noff, &x));
+    return handshake(2 * seq);
+  }
+  // k split (c == d): the GEMM stores this layer's partial product into its own buffer and, over NVLink, into the receive buffer
+  // every other layer keeps for it (alternating sets: a partner may already run product p + 1 while this layer still adds up p);
+  // one handshake later every layer holds all c partials and adds them in layer order.
+  const int64_t ldp = packed_ld(m);
+  if ((size_t)ldp * (size_t)n > D.precv_stride) {
+    ctx->set_error("distributed product: exchange buffers too small for a " + std::to_string(m) + " x " + std::to_string(n) + " product");
+    return CAPITAL_ERR_UNSUPPORTED;
+  }
+  double* recv_set = D.precv[q][seq & 1];
+  PartialSrc src{};
+  src.n = D.c;
+  for (int l = 0; l < D.c; l++) {
+    if (l == D.g.z) { src.p[l] = D.pown[q]; continue; }
+    const int oi = l < D.g.z ? l : l - 1;          // index of layer l among MY others
+    const int mi = D.g.z < l ? D.g.z : D.g.z - 1;  // index of my layer among layer l's others
+    x.Cpeer[oi] = peer_ptr(P, rank_of(D.g, D.g.x, D.g.y, l), recv_set + (size_t)mi * D.precv_stride);
+    src.p[l] = recv_set + (size_t)oi * D.precv_stride;
+  }
   if (D.dry) {
     for (int j = 0; j < D.nk; j++) { D.rd(sid, ops.A[j], ops.lda, k, m); D.rd(sid, ops.B[j], ops.ldb, k, n); }
-    const int64_t group = D.xmode ? (int64_t)(seq * 4 + q + 1) : 0;
-    D.wr(sid, D.me, Cown, C.M->ld, m, n, group);
-    for (int l = 0; l < D.c && D.xmode; l++)
-      if (l != D.g.z) D.wr(sid, rank_of(D.g, D.g.x, D.g.y, l), Cown, C.M->ld, m, n, group);
-    D.rec(T_PRODUCT, sid, q, (int64_t)seq, D.xmode);
-  } else CAP_TRY(gemm_tn_x(ctx, D.strm(sid), m, n, k, alpha, ops, beta, Cown, C.M->ld, flags, 0, noff, D.xmode ? &x : nullptr));
-  if (D.xmode) CAP_TRY(handshake(2 * seq));  // my kernel has retired => my stores are performed; the partners' flags say the same about theirs
+    D.wr(sid, D.me, D.pown[q], ldp, m, n);
+    for (int l = 0; l < D.c; l++)
+      if (l != D.g.z) D.wr(sid, rank_of(D.g, D.g.x, D.g.y, l), recv_set + (size_t)(D.g.z < l ? D.g.z : D.g.z - 1) * D.precv_stride, ldp, m, n);
+    D.rec(T_PRODUCT, sid, q, (int64_t)seq, 1);
+  } else CAP_TRY(gemm_tn_x(ctx, D.strm(sid), m, n, k, alpha, ops, 0.0, D.pown[q], ldp, flags, 0, noff, &x));
+  CAP_TRY(handshake(2 * seq));
+  if (D.dry) {
+    for (int l = 0; l < D.c; l++) D.rd(sid, src.p[l], ldp, m, n);
+    D.wr(sid, D.me, Cown, ldc, m, n);
+    D.rec(T_KERNEL, sid);
+  } else {
+    const int tli = ctx->tl_begin(D.strm(sid), 8, 4, (double)m, (double)n);
+    const long long r2 = (m + 1) / 2;
+    dim3 grid((unsigned)std::min<long long>(std::max<long long>(1, (r2 + 255) / 256), 64), (unsigned)std::min<int64_t>(n, 4 * (int64_t)ctx->num_sms));
+    reduce_partials_kernel<<<grid, 256, 0, D.strm(sid)>>>(m, n, src, ldp, beta, Cown, ldc, (flags & CAPITAL_GEMM_C_UPPER) ? 1 : 0, noff);
+    ctx->tl_end(D.strm(sid), tli);
+    ctx->counters.kernel_launches++;
+    CAP_CUDA(cudaGetLastError());
+  }
+  return CAPITAL_OK;
+}
+
+// The same product issued in `nch` column chunks of the output, each pushed to its consumers (roles != 0) as soon as it is complete:
+// the transfer of chunk j hides behind the GEMM of chunk j + 1 and only the last chunk's travel time stays exposed.
+capital_status_t product_pushed(Dist& D, int q, int64_t m, int64_t n, int64_t k, double alpha, Win X, Win Y, double beta, Win C, int flags,
+                                const Token* farX, const Token* farY, int roles, Token* last, int nch) {
+  if (nch < 1) nch = 1;
+  const int64_t cw = round_up(ceil_div(n, nch), 128);
+  for (int64_t c0 = 0; c0 < n; c0 += cw) {
+    const int64_t nc = std::min(cw, n - c0);
+    CAP_TRY(product(D, q, m, nc, k, alpha, X, Win{Y.M, Y.r0, Y.c0 + c0}, beta, Win{C.M, C.r0, C.c0 + c0}, flags, farX, farY, (int)c0));
+    if (roles) CAP_TRY(push(D, q, D.cstream(q), *C.M, C.r0, C.c0 + c0, m, nc, roles, last));
+  }
   return CAPITAL_OK;
 }
 
@@ -584,8 +679,8 @@ capital_status_t invoke(Dist& D, int64_t o, int64_t s, bool complete, int pendin
   // "trsm" via the inverse (cholinv.hpp:116-122): R12 = Rinv11^T A12
   CAP_TRY(need_cols(D, S_CHAIN, o + s));
   CAP_TRY(D.ev_wait(S_CHAIN, pending));
-  CAP_TRY(product(D, Q_CHAIN, s1, s2, s1, 1.0, Ri11, W12, 0.0, R12, CAPITAL_GEMM_A_UPPER, nullptr, &tW12));
-  CAP_TRY(push(D, Q_CHAIN, S_CHAIN, D.R, o, o + s1, s1, s2, ROLE_X | ROLE_Y, nullptr));
+  const int nch = (D.g.size > 1 && D.d > 1 && s2 >= D.chunk_min) ? D.chunks : 1;  // big blocks travel chunk by chunk behind the GEMM
+  CAP_TRY(product_pushed(D, Q_CHAIN, s1, s2, s1, 1.0, Ri11, W12, 0.0, R12, CAPITAL_GEMM_A_UPPER, nullptr, &tW12, ROLE_X | ROLE_Y, nullptr, nch));
   // trailing update (cholinv.hpp:131-134): A22 -= R12^T R12, upper tiles only.  near = what the right child's left subtree reads
   // (leading h x h block) stays on the chain, far = everything else goes to the deferred class.
   const int64_t h = node_splits(D, s2) ? (s2 >> D.split) : 0;
@@ -619,9 +714,8 @@ capital_status_t invoke(Dist& D, int64_t o, int64_t s, bool complete, int pendin
   if (complete) {
     CAP_TRY(D.ev_wait(S_CHAIN, e_tt));
     //   Rinv12 = -(T^T)^T Rinv22  (B = Ri22, upper triangular)   (cholinv.hpp:152-155)
-    CAP_TRY(product(D, Q_CHAIN, s1, s2, s2, -1.0, W21, Ri22, 0.0, Ri12, CAPITAL_GEMM_B_UPPER, &tTT, nullptr));
     Token tRi12;
-    CAP_TRY(push(D, Q_CHAIN, S_CHAIN, D.Ri, o, o + s1, s1, s2, ROLE_X | ROLE_Y | ROLE_T, &tRi12));
+    CAP_TRY(product_pushed(D, Q_CHAIN, s1, s2, s2, -1.0, W21, Ri22, 0.0, Ri12, CAPITAL_GEMM_B_UPPER, &tTT, nullptr, ROLE_X | ROLE_Y | ROLE_T, &tRi12, nch));
     CAP_TRY(transpose_dist(D, Q_CHAIN, D.Ri, o, o + s1, s1, s2, &tRi12, D.RiT.own + o * D.ld + (o + s1), D.ld));
     CAP_TRY(push(D, Q_CHAIN, S_CHAIN, D.RiT, o + s1, o, s2, s1, ROLE_Y, nullptr));
   }
@@ -673,14 +767,8 @@ size_t cholinv_layout(Dist& D, char* base) {
   layout_mat(lay, D, D.R, ld, L, ROLE_X | ROLE_Y, true);
   layout_mat(lay, D, D.Ri, ld, L, ROLE_X | ROLE_Y | ROLE_T, true);
   layout_mat(lay, D, D.RiT, ld, L, ROLE_Y, false);
-  D.precv_stride = 0;
-  if (D.xmode == 1) {
-    const int64_t s1 = L >> D.split, mx = std::max(s1, L - s1);
-    size_t bytes = 0, tiles = 0;
-    gemm_tn_xsizes(D.ctx, mx, mx, &bytes, &tiles);
-    D.precv_stride = bytes / 8;
-    for (int q = 0; q < PEER_QC; q++) D.precv[q] = lay.take(D.precv_stride * (size_t)(D.c - 1));
-  }
+  const int64_t s1top = L >> D.split, mx = std::max(s1top, L - s1top);
+  layout_exchange(lay, D, mx, mx, PEER_QC);
   D.gath_blk = 0;
   if (D.d > 1) {
     const int64_t s = std::max<int64_t>(D.bc_local, 1) * 2;  // base-case windows are <= 2 bc_local - 1 (a node splits above bc_local)
@@ -887,13 +975,7 @@ capital_status_t dist_cholinv_residual(capital_ctx* ctx, const double* A_local, 
     Layout lay(base);
     layout_mat(lay, D, E, ld, L, 0, false);
     layout_mat(lay, D, Rr, ld, L, ROLE_X | ROLE_Y, true);
-    D.precv_stride = 0;
-    if (D.xmode == 1) {
-      size_t bytes = 0, tiles = 0;
-      gemm_tn_xsizes(ctx, L, L, &bytes, &tiles);
-      D.precv_stride = bytes / 8;
-      for (int q = 0; q < PEER_QC; q++) D.precv[q] = q == Q_CHAIN ? lay.take(D.precv_stride * (size_t)(D.c - 1)) : nullptr;
-    }
+    layout_exchange(lay, D, L, L, 1);
     ar = lay.take((size_t)2 * g.size * 2);
     return lay.off;
   };
@@ -962,13 +1044,7 @@ capital_status_t dist_summa_gemm_tn(capital_ctx* ctx, int64_t m, int64_t n, int6
     layout_mat(lay, D, A, ldk, ml, ROLE_X, false);
     layout_mat(lay, D, B, ldk, nl, ROLE_Y, false);
     layout_mat(lay, D, C, ldm, nl, 0, false);
-    D.precv_stride = 0;
-    if (D.xmode == 1) {
-      size_t bytes = 0, tiles = 0;
-      gemm_tn_xsizes(ctx, ml, nl, &bytes, &tiles);
-      D.precv_stride = bytes / 8;
-      D.precv[Q_CHAIN] = lay.take(D.precv_stride * (size_t)(D.c - 1));
-    }
+    layout_exchange(lay, D, ml, nl, 1);
     return lay.off;
   };
   const size_t bytes = layout(nullptr);
@@ -1058,14 +1134,7 @@ size_t qr3_layout(Qr3& q, char* base) {
   layout_mat(lay, D, q.R2, ld, nl, ROLE_T, false);
   layout_mat(lay, D, q.Rt, ld, nl, ROLE_X, false);
   layout_mat(lay, D, q.Rf, ld, nl, 0, false);
-  D.precv_stride = 0;
-  if (D.xmode == 1) {
-    size_t b1 = 0, b2 = 0, tiles = 0;
-    gemm_tn_xsizes(D.ctx, nl, std::max(ml, nl), &b1, &tiles);
-    gemm_tn_xsizes(D.ctx, nl, nl, &b2, &tiles);
-    D.precv_stride = std::max(b1, b2) / 8;
-    for (int qq = 0; qq < PEER_QC; qq++) D.precv[qq] = lay.take(D.precv_stride * (size_t)(D.c - 1));
-  }
+  layout_exchange(lay, D, nl, std::max(ml, nl), PEER_QC);
   D.gath_blk = 0;
   if (D.d > 1) {
     const int64_t s = std::max<int64_t>(D.bc_local, 1) * 2;

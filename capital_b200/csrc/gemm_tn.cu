@@ -72,22 +72,6 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-// barrier over the consumer warps only (the producer warpgroup has left the kernel by then)
-__device__ __forceinline__ void consumer_bar(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
-
 constexpr int BK = 16;  // doubles per k tile = one 128-byte swizzle row
 
 // Warp roles: NCW consumer warps (whole warpgroups) + one producer warpgroup of which a single lane drives TMA.
@@ -105,25 +89,7 @@ __global__ void __launch_bounds__(((BM / WM) * (BN / WN) + 4) * 32, MINB)
   extern __shared__ uint8_t smem_raw[];
   const int flags = p.flags;
   const int gm = p.gm, gn = p.gn;
-  // Which tile?  Plain launches: the linear CTA id.  Mode 1: a ticket (CTAs start in ticket order whatever order the hardware
-  // dispatches them in); tickets [0, T) walk the tiles this layer does NOT own, [T, 2T) the ones it owns -- a ticket whose tile
-  // is of the other kind is a no-op.
-  int lin = (int)(blockIdx.x + gridDim.x * blockIdx.y);
-  bool owned_phase = false;
-  if (XMODE == 1) {
-    unsigned int* tk = reinterpret_cast<unsigned int*>(smem_raw);
-    const int T = gm * gn;
-    if (threadIdx.x == 0) {
-      const unsigned int mine = atomicAdd(p.x.ticket, 1u);
-      if (mine == 2u * (unsigned)T - 1u) *p.x.ticket = 0u;  // last ticket of this launch: re-arm the counter for the next product of the stream
-      *tk = mine;
-    }
-    __syncthreads();
-    const int t = (int)*tk;
-    __syncthreads();  // smem_raw is reused below
-    owned_phase = t >= T;
-    lin = owned_phase ? t - T : t;
-  }
+  const int lin = (int)(blockIdx.x + gridDim.x * blockIdx.y);
   // Longest-tile-first over the WHOLE grid: with a triangular operand the k extent depends on one tile coordinate only, so the
   // linear CTA id is mapped to tiles in order of decreasing k extent (row-major over the other coordinate).  The first wave then
   // holds the longest tiles and second residents / the tail get the short ones (a per-column reversal alone interleaves long and
@@ -134,11 +100,6 @@ __global__ void __launch_bounds__(((BM / WM) * (BN / WN) + 4) * 32, MINB)
   else if (flags & CAPITAL_GEMM_A_LOWER) { tm = lin / gn; tn = lin % gn; }
   else if (flags & CAPITAL_GEMM_B_LOWER) { tn = lin / gm; tm = lin % gm; }
   else { tm = lin % gm; tn = lin / gm; }
-  bool owner = true;
-  if (XMODE == 1) {
-    owner = ((tm + tn) % p.x.c) == p.x.z;
-    if (owner != owned_phase) return;
-  }
   if (XMODE == 2 && (tn % p.x.c) != p.x.z) return;  // another layer computes this tile column and stores it here
   const int m0 = tm * BM, n0 = tn * BN;
   const int n0g = n0 + p.noff;  // column position used by the structure tests
@@ -241,46 +202,7 @@ __global__ void __launch_bounds__(((BM / WM) * (BN / WN) + 4) * 32, MINB)
     if (lane == 0) mbar_arrive(empty0 + s * 8);
   }
 
-  // ---------------- depth exchange, mode 1: partial tiles travel in fragment order ----------------
   const int nother = (XMODE != 0) ? p.x.c - 1 : 0;
-  if (XMODE == 1) {
-    constexpr int NCT = NCW * 32;
-    const int ctid = threadIdx.x;  // consumer warps are warps 0 .. NCW-1
-    const long long tile_id = (long long)tm + (long long)gm * tn;
-    const long long tile_off = tile_id * (long long)(BM * BN);
-    if (!owner) {
-      const int zo = (tm + tn) % p.x.c, oi = zo < p.x.z ? zo : zo - 1;
-      double2* dst = reinterpret_cast<double2*>(p.x.precv_peer[oi] + tile_off);
-#pragma unroll
-      for (int i = 0; i < FM; i++)
-#pragma unroll
-        for (int j = 0; j < FN; j++) dst[(i * FN + j) * NCT + ctid] = make_double2(acc[i][j][0], acc[i][j][1]);
-      __threadfence_system();
-      consumer_bar(NCT);
-      if (ctid == 0) st_release_sys(p.x.tflag_peer[oi] + tile_id, p.x.seq);
-      return;
-    }
-    for (int oi = 0; oi < nother; oi++) {
-      if (ctid == 0) {
-        const unsigned long long* f = p.x.tflag_local[oi] + tile_id;
-        const unsigned long long t0 = globaltimer_ns();
-        while (ld_acquire_sys(f) < p.x.seq) {
-          __nanosleep(64);
-          if (globaltimer_ns() - t0 > 20000000000ull) { atomicExch(p.x.err, -1); break; }  // 20 s: a peer died; report instead of hanging
-        }
-      }
-      consumer_bar(NCT);
-      const double2* src = reinterpret_cast<const double2*>(p.x.precv_local[oi] + tile_off);
-#pragma unroll
-      for (int i = 0; i < FM; i++)
-#pragma unroll
-        for (int j = 0; j < FN; j++) {
-          const double2 v = __ldcg(src + (i * FN + j) * NCT + ctid);
-          acc[i][j][0] += v.x;
-          acc[i][j][1] += v.y;
-        }
-    }
-  }
 
   // ---------------- epilogue: C = alpha * acc + beta * C (to every replica when the exchange is on) ----------------
   const double alpha = p.alpha, beta = p.beta;
@@ -301,7 +223,7 @@ __global__ void __launch_bounds__(((BM / WM) * (BN / WN) + 4) * 32, MINB)
         if (XMODE == 0 && p.ksplit > 1) { atomicAdd(cc + row, v); continue; }
         if (beta != 0.0) v += beta * cc[row];
         cc[row] = v;
-        if (XMODE != 0) {
+        if (XMODE != 0) {  // mode 1: the partner's receive buffer for my partial; mode 2: the partner's replica of C
           for (int oi = 0; oi < nother; oi++) p.x.Cpeer[oi][coff + row] = v;
         }
       }
@@ -381,7 +303,7 @@ capital_status_t launch(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n,
   const int xmode = x ? x->mode : 0;
   if (xmode) p.x = *x;
   if (xmode == 1) {
-    dim3 grid((unsigned)(2 * p.gm * p.gn), 1, 1);
+    dim3 grid((unsigned)p.gm, (unsigned)p.gn, 1);
     Cfg::template kernel<1>()<<<grid, Cfg::threads, Cfg::smem, st>>>(maps, p);
   } else if (xmode == 2) {
     dim3 grid((unsigned)p.gm, (unsigned)p.gn, 1);
@@ -443,14 +365,8 @@ capital_status_t gemm_tn_init(capital_ctx* ctx) {
   return CAPITAL_OK;
 }
 
-// which tile configuration a product of this output shape runs with (the same on every layer: exchange buffers are tile-indexed)
+// which tile configuration a product of this output shape runs with
 static inline bool gemm_uses_big(const capital_ctx* ctx, int64_t m, int64_t n) { return ceil_div(m, 128) * ceil_div(n, 128) >= ctx->num_sms; }
-void gemm_tn_xsizes(const capital_ctx* ctx, int64_t m, int64_t n, size_t* precv_bytes, size_t* tiles) {
-  const int64_t b = gemm_uses_big(ctx, m, n) ? 128 : 64;
-  const int64_t t = ceil_div(m, b) * ceil_div(n, b);
-  *tiles = (size_t)t;
-  *precv_bytes = (size_t)t * b * b * 8;
-}
 
 // Split-K variant for short-and-fat products (the tall-skinny Gram matrix, cacqr.hpp:15): C += alpha A^T B with the
 // k range cut into `ksplit` chunks, partial tiles accumulated with FP64 atomics.  C must hold the addend on entry.
@@ -511,6 +427,7 @@ capital_status_t gemm_tn_x(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t
   if (k == 0) { ctx->set_error("gemm_tn: k must be positive"); return CAPITAL_ERR_INVALID; }
   if (m >= (1LL << 31) || n >= (1LL << 31) || k >= (1LL << 31) - 16) return CAPITAL_ERR_INVALID;
   if (x && x->mode && (x->c < 2 || x->c - 1 > GEMM_XPEERS_MAX)) { ctx->set_error("gemm_tn: exchange over more than 4 layers"); return CAPITAL_ERR_UNSUPPORTED; }
+  if (x && x->mode == 1 && beta != 0.0) { ctx->set_error("gemm_tn: a partial product (mode 1) cannot accumulate"); return CAPITAL_ERR_INVALID; }
   ctx->counters.kernel_launches++;
   ctx->counters.gemm_launches++;
   // algorithmic flops of this product on THIS device (structure exploited exactly, not tile-rounded)

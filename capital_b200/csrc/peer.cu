@@ -94,6 +94,41 @@ __global__ void ar_sum_kernel(double* __restrict__ buf, long long count, const d
   }
 }
 
+// stream memory operations (driver API, resolved at run time: the library does not link libcuda)
+typedef CUresult (*fn_batch)(CUstream, unsigned int, CUstreamBatchMemOpParams*, unsigned int);
+fn_batch g_batch = nullptr;
+bool memops_load() {
+  if (g_batch) return true;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuStreamBatchMemOp", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return false;
+  g_batch = (fn_batch)p;
+  return true;
+}
+capital_status_t memops_issue(capital_ctx* ctx, cudaStream_t st, const FlagList& fl, bool wait) {
+  CUstreamBatchMemOpParams ops[24];
+  memset(ops, 0, sizeof(ops));
+  for (int i = 0; i < fl.n; i++) {
+    if (wait) {
+      ops[i].waitValue.operation = CU_STREAM_MEM_OP_WAIT_VALUE_64;
+      ops[i].waitValue.address = (CUdeviceptr)fl.p[i];
+      ops[i].waitValue.value64 = fl.v[i];
+      ops[i].waitValue.flags = CU_STREAM_WAIT_VALUE_GEQ;
+    } else {
+      ops[i].writeValue.operation = CU_STREAM_MEM_OP_WRITE_VALUE_64;
+      ops[i].writeValue.address = (CUdeviceptr)fl.p[i];
+      ops[i].writeValue.value64 = fl.v[i];
+      ops[i].writeValue.flags = CU_STREAM_WRITE_VALUE_DEFAULT;  // ordered after (fenced against) the stream's earlier writes
+    }
+  }
+  const CUresult r = g_batch((CUstream)st, (unsigned)fl.n, ops, 0);
+  if (r != CUDA_SUCCESS) {
+    ctx->set_error("cuStreamBatchMemOp failed: CUresult " + std::to_string((int)r));
+    return CAPITAL_ERR_CUDA;
+  }
+  return CAPITAL_OK;
+}
+
 capital_status_t exchange(capital_ctx* ctx, const void* mine, void* all, int64_t bytes) {
   Peer* P = peer_of(ctx);
   const int rc = P->ag(P->ag_user, mine, all, bytes);
@@ -124,8 +159,8 @@ capital_status_t peer_init(capital_ctx* ctx, peer_allgather_fn ag, void* user) {
   P->size = g.size; P->rank = g.rank; P->ag = ag; P->ag_user = user;
   CAP_CUDA(cudaMalloc(&P->ctrl, CTRL_WORDS * 8));
   CAP_CUDA(cudaMemset(P->ctrl, 0, CTRL_WORDS * 8));
-  CAP_CUDA(cudaMalloc(&P->tickets, PEER_QC * sizeof(unsigned int)));
-  CAP_CUDA(cudaMemset(P->tickets, 0, PEER_QC * sizeof(unsigned int)));
+  if (const char* e = getenv("CAPITAL_PEER_MEMOPS")) P->memops = atoi(e) != 0;
+  if (P->memops && !memops_load()) P->memops = false;
   cudaIpcMemHandle_t mine;
   CAP_CUDA(cudaIpcGetMemHandle(&mine, P->ctrl));
   std::vector<cudaIpcMemHandle_t> all(g.size);
@@ -153,7 +188,6 @@ void peer_destroy(capital_ctx* ctx) {
   }
   if (P->arena) cudaFree(P->arena);
   if (P->ctrl) cudaFree(P->ctrl);
-  if (P->tickets) cudaFree(P->tickets);
   if (P->d_stage) cudaFree(P->d_stage);
   for (int q = 0; q < PEER_Q; q++) if (P->push[q]) cudaStreamDestroy(P->push[q]);
   if (ctx->comm_world && nccl().lib) nccl().CommDestroy((ncclComm_t)ctx->comm_world);
@@ -201,6 +235,11 @@ capital_status_t peer_arena_reserve(capital_ctx* ctx, size_t bytes) {
 capital_status_t peer_signal(capital_ctx* ctx, cudaStream_t st, const FlagList& fl) {
   if (fl.n == 0) return CAPITAL_OK;
   const int tli = ctx->tl_begin(st, 6, fl.n);
+  if (peer_of(ctx)->memops) {
+    const capital_status_t rs = memops_issue(ctx, st, fl, false);
+    ctx->tl_end(st, tli);
+    return rs;
+  }
   signal_kernel<<<1, 32, 0, st>>>(fl);
   ctx->tl_end(st, tli);
   ctx->counters.kernel_launches++;
@@ -210,6 +249,11 @@ capital_status_t peer_signal(capital_ctx* ctx, cudaStream_t st, const FlagList& 
 capital_status_t peer_wait(capital_ctx* ctx, cudaStream_t st, const FlagList& fl) {
   if (fl.n == 0) return CAPITAL_OK;
   const int tli = ctx->tl_begin(st, 5, fl.n);
+  if (peer_of(ctx)->memops) {
+    const capital_status_t rs = memops_issue(ctx, st, fl, true);
+    ctx->tl_end(st, tli);
+    return rs;
+  }
   wait_kernel<<<1, 32, 0, st>>>(fl, ctx->d_info);
   ctx->tl_end(st, tli);
   ctx->counters.kernel_launches++;

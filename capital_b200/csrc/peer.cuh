@@ -4,7 +4,8 @@
 // cudaMalloc'ed, exported with cudaIpcGetMemHandle and mapped by every other rank, so that any rank can
 //   * DMA a finished block into a consumer's mirror buffer (copy engines, cudaMemcpy2DAsync on a push stream),
 //   * store GEMM partials / final tiles straight from the epilogue into a depth partner's memory (gemm_tn.cu, GemmXDev),
-//   * raise a flag in another rank's control block (st.release.sys) and wait on its own flags (ld.acquire.sys).
+//   * raise a flag in another rank's control block and wait on its own flags -- stream memory operations
+//     (cuStreamWriteValue64 / cuStreamWaitValue64: no SM is needed, so a flag is never stuck behind the CTAs of a running GEMM).
 // The arena layout is a pure function of the problem shape and of the grid, identical on every rank, so an offset computed
 // locally addresses the same object in every peer's arena ("symmetric heap").  Flags carry monotonically increasing sequence
 // numbers (never reset), which makes "wait until flag >= v" race-free across repeated factorizations.
@@ -18,14 +19,12 @@
 constexpr int PEER_MAX_RANKS = 16;
 constexpr int PEER_Q = 3;                    // flag / push-stream classes: 0 = critical chain, 1 = deferred ("far") work, 2 = bulk pushes (node-entry operands)
 constexpr int PEER_QC = 2;                   // classes that run fused products (own compute stream, receive buffers, tile flags)
-constexpr int PEER_TILEFLAGS = 1 << 16;      // per (class, other layer): tiles of one fused product
 // control block layout (units of 8 bytes)
 constexpr size_t CTRL_PUSH = 0;                                   // [src][q]   "all I pushed to you on class q up to id v has landed"
 constexpr size_t CTRL_DONE = CTRL_PUSH + PEER_MAX_RANKS * PEER_Q; // [src][q]   "my fused product v on class q has retired"
 constexpr size_t CTRL_BAR = CTRL_DONE + PEER_MAX_RANKS * PEER_Q;  // [src]      world barrier epochs
 constexpr size_t CTRL_AR = CTRL_BAR + PEER_MAX_RANKS;             // [src]      small all-reduce epochs
-constexpr size_t CTRL_TILE = 128;                                 // [q][other layer][tile]
-constexpr size_t CTRL_WORDS = CTRL_TILE + (size_t)PEER_QC * GEMM_XPEERS_MAX * PEER_TILEFLAGS;
+constexpr size_t CTRL_WORDS = 256;
 
 typedef int (*peer_allgather_fn)(void* user, const void* send, void* recv, int64_t bytes_per_rank);
 
@@ -49,7 +48,7 @@ struct Peer {
   unsigned long long push_id[PEER_Q] = {0, 0, 0};   // logical push events issued so far (same on every rank)
   unsigned long long prod_seq[PEER_QC] = {0, 0};    // fused products issued so far
   unsigned long long bar_epoch = 0, ar_epoch = 0;
-  unsigned int* tickets = nullptr;               // one self-resetting tile-ticket counter per stream class
+  bool memops = true;   // flags through stream memory operations (no SM needed) instead of one-warp kernels [env CAPITAL_PEER_MEMOPS]
   // NCCL bootstrap (only when capital_comm_init was used)
   void* d_stage = nullptr;
 };
@@ -68,8 +67,8 @@ template <typename T>
 inline T* peer_ptr(const Peer* P, int r, T* p) { return r == P->rank ? p : (T*)(P->peer_arena[r] + ((char*)p - P->arena)); }
 inline unsigned long long* ctrl_ptr(const Peer* P, int r, size_t word) { return (r == P->rank ? P->ctrl : P->peer_ctrl[r]) + word; }
 
-capital_status_t peer_signal(capital_ctx* ctx, cudaStream_t st, const FlagList& fl);  // remote (or local) flag stores, release.sys
-capital_status_t peer_wait(capital_ctx* ctx, cudaStream_t st, const FlagList& fl);    // spin on LOCAL flags, acquire.sys; 20 s timeout -> d_info = -1
+capital_status_t peer_signal(capital_ctx* ctx, cudaStream_t st, const FlagList& fl);  // remote (or local) flag stores, ordered after the stream's earlier work
+capital_status_t peer_wait(capital_ctx* ctx, cudaStream_t st, const FlagList& fl);    // the stream stalls until every LOCAL flag has reached its value
 capital_status_t peer_barrier(capital_ctx* ctx, cudaStream_t st);                     // all ranks: everything enqueued on `st` before has completed everywhere
 // sum of `count` doubles over all ranks, in rank order on every rank (bit-identical results); `slots` = arena region of
 // 2 * size * count doubles

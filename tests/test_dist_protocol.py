@@ -3,8 +3,7 @@
 `capital_dist_trace_cholinv` dry-runs the REAL schedule code of one rank: every flag wait / signal, fused product, event
 record / wait, peer DMA and arena window access it would enqueue for two consecutive cholinv::factor calls.  The traces of all
 ranks of a grid are replayed here under CUDA's ordering rules (streams are FIFO; an event wait waits for the record that preceded
-it; a flag wait spins until the flag reaches the value; a k-split fused product cannot retire before its depth partners have
-started the same product) and checked for
+it; a flag wait stalls the stream until the flag reaches the value) and checked for
   * deadlock freedom: the replay must drain every stream of every rank;
   * data races: two accesses to overlapping windows of the same rank's arena, at least one a write, must be ordered by
     happens-before (vector clocks) -- i.e. every operand a product reads from a mirror slot was pushed AND waited for, and
@@ -98,25 +97,10 @@ class Replay:
             self.clock[r][s] = np.maximum(clk, e)
             self.tick(r, s)
         elif kind == T_PRODUCT:
-            qq, seq, mode = op[2], op[3], op[4]
-            if mode == 1:
-                # the kernel starts as soon as it is at the head of its stream; it cannot retire before its depth partners have
-                # STARTED the same product (it needs their partial tiles).  Its accesses span [start, retire].
-                key = (r, qq, seq)
-                if key not in self.started:
-                    self.started[key] = self.tick(r, s)
-                need = [self.started.get((p, qq, seq)) for p in self.partners(r, grid)]
-                if any(n is None for n in need):
-                    return False
-                c = self.clock[r][s]
-                for n in need:
-                    c = np.maximum(c, n)
-                self.clock[r][s] = c
-                self.tick(r, s)
-                self.flush_accesses(r, s, start=self.started[key])
-            else:
-                self.tick(r, s)
-                self.flush_accesses(r, s)
+            # a GEMM launch: it needs nothing from other ranks while it runs (partials / final tiles are stored into the partners'
+            # buffers, the handshake that follows is explicit flag traffic)
+            self.tick(r, s)
+            self.flush_accesses(r, s)
         elif kind in (T_READ, T_WRITE):
             self.pending_acc[r][s].append(op)
         else:  # T_DMA, T_KERNEL
@@ -196,6 +180,7 @@ def test_flag_protocol_is_deadlock_free_and_race_free(size, n, ci, bcm, monkeypa
     # small nodes must exercise the deferred class too
     monkeypatch.setenv("CAPITAL_DIST_FAR_MIN", "64")
     monkeypatch.setenv("CAPITAL_DIST_SIDE_MIN", "32")
+    monkeypatch.setenv("CAPITAL_DIST_CHUNK_MIN", "256")  # ... and the chunked, pushed products
     c, d = GRIDS[size]
     traces = [trace(size, r, c, n, ci, bcm) for r in range(size)]
     rp = Replay(traces)
