@@ -23,12 +23,14 @@ capital_status_t capital_ctx::workspace(const std::string& name, size_t bytes, v
 int capital_ctx::stream_id(cudaStream_t st) const {
   if (st == hi) return 1;
   if (st == side) return 2;
+  if (st == side_deep[0]) return 3;
+  if (st == side_deep[1]) return 4;
   if (peer) {
     const Peer* P = (const Peer*)peer;
-    for (int q = 0; q < PEER_Q; q++) if (st == P->push[q]) return 3 + q;
+    for (int q = 0; q < PEER_Q; q++) if (st == P->push[q]) return 5 + q;
   }
-  if (st == copy_in) return 6;
-  if (st == copy_out) return 7;
+  if (st == copy_in) return 10;
+  if (st == copy_out) return 11;
   return 0;
 }
 int capital_ctx::tl_begin(cudaStream_t st, int kind, double a, double b, double c) {
@@ -291,9 +293,13 @@ static bool make_green_side_stream(capital_ctx* ctx, int reserve, int prio) {
   if (((fn_desc)p4)(&desc, far.data(), (unsigned)far.size()) != CUDA_SUCCESS) return false;
   CUgreenCtx g;
   if (((fn_gcreate)p5)(&g, desc, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
-  CUstream gs;
+  CUstream gs, gd[2];
   if (((fn_gstream)p6)(&gs, g, CU_STREAM_NON_BLOCKING, prio) != CUDA_SUCCESS) return false;
+  for (int i = 0; i < 2; i++)
+    if (((fn_gstream)p6)(&gd[i], g, CU_STREAM_NON_BLOCKING, prio - 1 - i) != CUDA_SUCCESS) return false;
   ctx->side = (cudaStream_t)gs;
+  ctx->side_deep[0] = (cudaStream_t)gd[0];
+  ctx->side_deep[1] = (cudaStream_t)gd[1];
   ctx->green = (void*)g;
   ctx->side_sms = 0;
   for (auto& r : far) ctx->side_sms += (int)r.sm.smCount;
@@ -323,8 +329,10 @@ capital_status_t capital_create(capital_ctx** out, const capital_grid_t* grid, i
   int reserve = 8;  // SMs kept free of deferred work [env CAPITAL_GREEN_SMS; 0 = plain low-priority stream]
   if (const char* e = getenv("CAPITAL_GREEN_SMS")) reserve = atoi(e);
   bool ok = true;
-  if (reserve <= 0 || !make_green_side_stream(ctx, reserve, prio_lo))
+  if (reserve <= 0 || !make_green_side_stream(ctx, reserve, prio_lo)) {
     ok = cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, prio_lo) == cudaSuccess;
+    for (int i = 0; i < 2; i++) ok = ok && cudaStreamCreateWithPriority(&ctx->side_deep[i], cudaStreamNonBlocking, prio_lo - 1 - i) == cudaSuccess;
+  }
   ok = ok && cudaStreamCreateWithPriority(&ctx->hi, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking) == cudaSuccess;
@@ -366,6 +374,7 @@ void capital_destroy(capital_ctx* ctx) {
   for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
   for (cudaEvent_t e : ctx->tl_pool) cudaEventDestroy(e);
   if (ctx->side) cudaStreamDestroy(ctx->side);
+  for (int i = 0; i < 2; i++) if (ctx->side_deep[i]) cudaStreamDestroy(ctx->side_deep[i]);
   if (ctx->green) {
     typedef CUresult (*fn_gdestroy)(CUgreenCtx);
     void* pd = nullptr;

@@ -44,6 +44,7 @@ struct capital_ctx {
   cudaStream_t side = nullptr;     // low-priority stream: deferred ("far") trailing updates, T^T products; lives in a green context
   void* green = nullptr;           // (CUgreenCtx) SM partition of the deferred stream, see make_green_side_stream (api.cu)
   int side_sms = 0;                // SMs of that partition (0: no partition)
+  cudaStream_t side_deep[2] = {nullptr, nullptr};  // deferred streams of recursion depths 1 and 2 (multi-GPU schedule), same partition, rising priority
   cudaStream_t hi = nullptr;       // high-priority stream: the critical chain of the recursion
   cudaStream_t copy_in = nullptr, copy_out = nullptr;  // H2D / D2H streams of the host-pointer path
   // EXPERIMENTAL, off by default [env CAPITAL_ZC_OUT=1]: host outputs leave block by block through a kernel that stores straight
@@ -98,7 +99,7 @@ struct capital_ctx {
   std::vector<TlRec> tl;
   std::vector<cudaEvent_t> tl_pool;
   size_t tl_used = 0;
-  int stream_id(cudaStream_t st) const;  // 0 caller, 1 chain, 2 deferred, 3.. push streams, 6 copy-in, 7 copy-out
+  int stream_id(cudaStream_t st) const;  // 0 caller, 1 chain, 2-4 deferred (depth 0-2), 5-9 push streams, 10 copy-in, 11 copy-out
   int tl_begin(cudaStream_t st, int kind, double a = 0, double b = 0, double c = 0);
   void tl_end(cudaStream_t st, int idx);
 

@@ -105,8 +105,8 @@ inline int64_t packed_ld(int64_t rows) { return round_up(rows, 2); }
 
 // ---- the distributed machinery --------------------------------------------------------------------------------
 enum { ROLE_X = 1, ROLE_Y = 2, ROLE_T = 4, ROLE_G = 8 };
-enum { Q_CHAIN = 0, Q_FAR = 1, Q_BULK = 2 };
-enum { S_USER = 0, S_CHAIN = 1, S_FAR = 2, S_PUSH0 = 3, S_PUSH1 = 4, S_PUSH2 = 5, S_COPYIN = 6, S_COPYOUT = 7, S_COUNT = 8 };
+enum { Q_CHAIN = 0, Q_FAR0 = 1, Q_BULK = PEER_QC };  // deferred classes Q_FAR0 + depth, depth < PEER_NFAR
+enum { S_USER = 0, S_CHAIN = 1, S_FAR0 = 2, S_PUSH0 = S_FAR0 + PEER_NFAR, S_COPYIN = S_PUSH0 + PEER_Q, S_COPYOUT = S_COPYIN + 1, S_COUNT = S_COPYOUT + 1 };
 constexpr int NK_MAX = GEMM_NCLS_MAX;
 
 // A matrix that lives in the arena together with its mirror slots: xs[j] / ys[j] receive the blocks of the class-j X / Y source,
@@ -160,9 +160,9 @@ struct Dist {
   DMat W, R, Ri, RiT;
   // partial products of the k-split exchange, per stream class: my own partial, and two alternating sets of receive buffers (one
   // per other layer) that the partners' GEMM epilogues store into
-  double* pown[PEER_QC] = {nullptr, nullptr};
-  double* precv[PEER_QC][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
-  size_t precv_stride = 0;  // doubles per partial buffer
+  double* pown[PEER_QC] = {};
+  double* precv[PEER_QC][2] = {};
+  size_t precv_stride[PEER_QC] = {};  // doubles per partial buffer of the class
   double* gath[2] = {nullptr, nullptr};
   int64_t gath_blk = 0;
   unsigned long long bc_count = 0;
@@ -186,15 +186,15 @@ struct Dist {
     switch (sid) {
       case S_USER: return ctx->stream;
       case S_CHAIN: return ctx->hi;
-      case S_FAR: return ctx->side;
-      case S_PUSH0: return P->push[0];
-      case S_PUSH1: return P->push[1];
-      case S_PUSH2: return P->push[2];
+      case S_FAR0: return ctx->side;
+      case S_FAR0 + 1: return ctx->side_deep[0];
+      case S_FAR0 + 2: return ctx->side_deep[1];
       case S_COPYIN: return ctx->copy_in;
-      default: return ctx->copy_out;
+      case S_COPYOUT: return ctx->copy_out;
+      default: return P->push[sid - S_PUSH0];
     }
   }
-  int cstream(int q) const { return q == Q_CHAIN ? S_CHAIN : S_FAR; }
+  int cstream(int q) const { return q == Q_CHAIN ? S_CHAIN : S_FAR0 + (q - Q_FAR0); }
   void rec(int kind, int sid, int64_t a = 0, int64_t b = 0, int64_t c_ = 0, int64_t d_ = 0, int64_t e_ = 0, int64_t f_ = 0) {
     const int64_t r[TREC] = {kind, sid, a, b, c_, d_, e_, f_};
     trace->insert(trace->end(), r, r + TREC);
@@ -366,15 +366,13 @@ void layout_mat(Layout& lay, const Dist& D, DMat& M, int64_t ld, int64_t cols, i
   }
 }
 
-// partial-product buffers of the k-split exchange for products up to m x n, for the first `classes` stream classes
-void layout_exchange(Layout& lay, Dist& D, int64_t m, int64_t n, int classes) {
-  D.precv_stride = 0;
+// partial-product buffers of the k-split exchange of one stream class, for products of up to `elems` output elements
+void layout_exchange(Layout& lay, Dist& D, int q, int64_t m, int64_t n) {
+  D.precv_stride[q] = 0;
   if (D.xmode != 1) return;
-  D.precv_stride = (size_t)round_up((int64_t)((size_t)packed_ld(m) * n), 128);
-  for (int q = 0; q < classes; q++) {
-    D.pown[q] = lay.take(D.precv_stride);
-    for (int b = 0; b < 2; b++) D.precv[q][b] = lay.take(D.precv_stride * (size_t)(D.c - 1));
-  }
+  D.precv_stride[q] = (size_t)round_up((int64_t)((size_t)packed_ld(m) * n), 128);
+  D.pown[q] = lay.take(D.precv_stride[q]);
+  for (int b = 0; b < 2; b++) D.precv[q][b] = lay.take(D.precv_stride[q] * (size_t)(D.c - 1));
 }
 
 // ---- push: a finished block goes to everybody who will read it ----------------------------------------------------------
@@ -494,7 +492,8 @@ capital_status_t product(Dist& D, int q, int64_t m, int64_t n, int64_t k, double
   // every other layer keeps for it (alternating sets: a partner may already run product p + 1 while this layer still adds up p);
   // one handshake later every layer holds all c partials and adds them in layer order.
   const int64_t ldp = packed_ld(m);
-  if ((size_t)ldp * (size_t)n > D.precv_stride) {
+  const size_t stride = D.precv_stride[q];
+  if ((size_t)ldp * (size_t)n > stride) {
     ctx->set_error("distributed product: exchange buffers too small for a " + std::to_string(m) + " x " + std::to_string(n) + " product");
     return CAPITAL_ERR_UNSUPPORTED;
   }
@@ -505,14 +504,14 @@ capital_status_t product(Dist& D, int q, int64_t m, int64_t n, int64_t k, double
     if (l == D.g.z) { src.p[l] = D.pown[q]; continue; }
     const int oi = l < D.g.z ? l : l - 1;          // index of layer l among MY others
     const int mi = D.g.z < l ? D.g.z : D.g.z - 1;  // index of my layer among layer l's others
-    x.Cpeer[oi] = peer_ptr(P, rank_of(D.g, D.g.x, D.g.y, l), recv_set + (size_t)mi * D.precv_stride);
-    src.p[l] = recv_set + (size_t)oi * D.precv_stride;
+    x.Cpeer[oi] = peer_ptr(P, rank_of(D.g, D.g.x, D.g.y, l), recv_set + (size_t)mi * stride);
+    src.p[l] = recv_set + (size_t)oi * stride;
   }
   if (D.dry) {
     for (int j = 0; j < D.nk; j++) { D.rd(sid, ops.A[j], ops.lda, k, m); D.rd(sid, ops.B[j], ops.ldb, k, n); }
     D.wr(sid, D.me, D.pown[q], ldp, m, n);
     for (int l = 0; l < D.c; l++)
-      if (l != D.g.z) D.wr(sid, rank_of(D.g, D.g.x, D.g.y, l), recv_set + (size_t)(D.g.z < l ? D.g.z : D.g.z - 1) * D.precv_stride, ldp, m, n);
+      if (l != D.g.z) D.wr(sid, rank_of(D.g, D.g.x, D.g.y, l), recv_set + (size_t)(D.g.z < l ? D.g.z : D.g.z - 1) * stride, ldp, m, n);
     D.rec(T_PRODUCT, sid, q, (int64_t)seq, 1);
   } else CAP_TRY(gemm_tn_x(ctx, D.strm(sid), m, n, k, alpha, ops, 0.0, D.pown[q], ldp, flags, 0, noff, &x));
   CAP_TRY(handshake(2 * seq));
@@ -684,31 +683,35 @@ capital_status_t invoke(Dist& D, int64_t o, int64_t s, bool complete, int pendin
   // trailing update (cholinv.hpp:131-134): A22 -= R12^T R12, upper tiles only.  near = what the right child's left subtree reads
   // (leading h x h block) stays on the chain, far = everything else goes to the deferred class.
   const int64_t h = node_splits(D, s2) ? (s2 >> D.split) : 0;
-  const bool use_side = D.two_stream && s1 >= D.side_min;
+  // deferred class of this depth (own stream, exchange buffers, flags): a deeper node's deferred work is wanted sooner than its
+  // ancestors' and would be stuck behind it on a shared FIFO stream; below depth PEER_NFAR everything stays on the chain
+  const int fq = depth < PEER_NFAR ? Q_FAR0 + depth : -1;
+  const bool use_side = D.two_stream && fq >= 0 && s1 >= D.side_min;
+  const int fs = use_side ? D.cstream(fq) : S_CHAIN;
   int e_r12 = -1, e_far = -1, e_tt = -1;
   Token tChildW12{}, tTT{};
   if (use_side) {
     CAP_TRY(D.ev_record(S_CHAIN, &e_r12));
-    CAP_TRY(D.ev_wait(S_FAR, e_r12));
+    CAP_TRY(D.ev_wait(fs, e_r12));
   }
   if (use_side && h > 0 && s2 >= D.far_min) {
     const Win R12b{&D.R, o, o + s1 + h};
     CAP_TRY(product(D, Q_CHAIN, h, h, s1, -1.0, R12, R12, 1.0, W22, CAPITAL_GEMM_C_UPPER));
-    CAP_TRY(product(D, Q_FAR, h, s2 - h, s1, -1.0, R12, R12b, 1.0, Win{&D.W, o + s1, o + s1 + h}, 0));
+    CAP_TRY(product(D, fq, h, s2 - h, s1, -1.0, R12, R12b, 1.0, Win{&D.W, o + s1, o + s1 + h}, 0));
     // that block is the right child's A12: its Y consumers get it as soon as it is final
-    CAP_TRY(push(D, Q_FAR, S_FAR, D.W, o + s1, o + s1 + h, h, s2 - h, ROLE_Y, &tChildW12));
-    CAP_TRY(product(D, Q_FAR, s2 - h, s2 - h, s1, -1.0, R12b, R12b, 1.0, Win{&D.W, o + s1 + h, o + s1 + h}, CAPITAL_GEMM_C_UPPER));
-    CAP_TRY(D.ev_record(S_FAR, &e_far));
+    CAP_TRY(push(D, fq, fs, D.W, o + s1, o + s1 + h, h, s2 - h, ROLE_Y, &tChildW12));
+    CAP_TRY(product(D, fq, s2 - h, s2 - h, s1, -1.0, R12b, R12b, 1.0, Win{&D.W, o + s1 + h, o + s1 + h}, CAPITAL_GEMM_C_UPPER));
+    CAP_TRY(D.ev_record(fs, &e_far));
   } else {
     CAP_TRY(product(D, Q_CHAIN, s2, s2, s1, -1.0, R12, R12, 1.0, W22, CAPITAL_GEMM_C_UPPER));
   }
   if (complete) {
     // inverse combine, first half (cholinv.hpp:151): T^T = R12^T Rinv11^T  (B = RiT11, lower triangular) -- nobody needs it before
     // the right child is done
-    const int qt = use_side ? Q_FAR : Q_CHAIN;
+    const int qt = use_side ? fq : Q_CHAIN;
     CAP_TRY(product(D, qt, s2, s1, s1, 1.0, R12, RiT11, 0.0, W21, CAPITAL_GEMM_B_LOWER));
     CAP_TRY(push(D, qt, D.cstream(qt), D.W, o + s1, o, s2, s1, ROLE_X, &tTT));
-    if (use_side) CAP_TRY(D.ev_record(S_FAR, &e_tt));
+    if (use_side) CAP_TRY(D.ev_record(fs, &e_tt));
   }
   CAP_TRY(invoke(D, o + s1, s2, true, e_far, tChildW12, depth + 1));
   if (complete) {
@@ -743,14 +746,14 @@ capital_status_t fork_streams(Dist& D) {
   int e;
   CAP_TRY(D.ev_record(S_USER, &e));
   for (int sid = S_CHAIN; sid < S_COUNT; sid++) {
-    if (D.g.size == 1 && sid >= S_PUSH0 && sid <= S_PUSH2) continue;
+    if (D.g.size == 1 && sid >= S_PUSH0 && sid < S_COPYIN) continue;
     CAP_TRY(D.ev_wait(sid, e));
   }
   return CAPITAL_OK;
 }
 capital_status_t join_streams(Dist& D) {
   for (int sid = S_CHAIN; sid < S_COUNT; sid++) {
-    if (D.g.size == 1 && sid >= S_PUSH0 && sid <= S_PUSH2) continue;
+    if (D.g.size == 1 && sid >= S_PUSH0 && sid < S_COPYIN) continue;
     int e;
     CAP_TRY(D.ev_record(sid, &e));
     CAP_TRY(D.ev_wait(S_USER, e));
@@ -767,8 +770,13 @@ size_t cholinv_layout(Dist& D, char* base) {
   layout_mat(lay, D, D.R, ld, L, ROLE_X | ROLE_Y, true);
   layout_mat(lay, D, D.Ri, ld, L, ROLE_X | ROLE_Y | ROLE_T, true);
   layout_mat(lay, D, D.RiT, ld, L, ROLE_Y, false);
-  const int64_t s1top = L >> D.split, mx = std::max(s1top, L - s1top);
-  layout_exchange(lay, D, mx, mx, PEER_QC);
+  // the chain multiplies blocks of every level; the deferred class of depth k only the trailing-update and T^T blocks of that depth
+  int64_t sz = L;
+  for (int q = 0; q < PEER_QC; q++) {
+    const int64_t s1q = sz >> D.split, mx = std::max(s1q, sz - s1q) + 2;
+    layout_exchange(lay, D, q, mx, mx);
+    if (q >= Q_FAR0) sz = sz - s1q;  // the right child is the larger one
+  }
   D.gath_blk = 0;
   if (D.d > 1) {
     const int64_t s = std::max<int64_t>(D.bc_local, 1) * 2;  // base-case windows are <= 2 bc_local - 1 (a node splits above bc_local)
@@ -975,7 +983,7 @@ capital_status_t dist_cholinv_residual(capital_ctx* ctx, const double* A_local, 
     Layout lay(base);
     layout_mat(lay, D, E, ld, L, 0, false);
     layout_mat(lay, D, Rr, ld, L, ROLE_X | ROLE_Y, true);
-    layout_exchange(lay, D, L, L, 1);
+    layout_exchange(lay, D, Q_CHAIN, L, L);
     ar = lay.take((size_t)2 * g.size * 2);
     return lay.off;
   };
@@ -1044,7 +1052,7 @@ capital_status_t dist_summa_gemm_tn(capital_ctx* ctx, int64_t m, int64_t n, int6
     layout_mat(lay, D, A, ldk, ml, ROLE_X, false);
     layout_mat(lay, D, B, ldk, nl, ROLE_Y, false);
     layout_mat(lay, D, C, ldm, nl, 0, false);
-    layout_exchange(lay, D, ml, nl, 1);
+    layout_exchange(lay, D, Q_CHAIN, ml, nl);
     return lay.off;
   };
   const size_t bytes = layout(nullptr);
@@ -1134,7 +1142,7 @@ size_t qr3_layout(Qr3& q, char* base) {
   layout_mat(lay, D, q.R2, ld, nl, ROLE_T, false);
   layout_mat(lay, D, q.Rt, ld, nl, ROLE_X, false);
   layout_mat(lay, D, q.Rf, ld, nl, 0, false);
-  layout_exchange(lay, D, nl, std::max(ml, nl), PEER_QC);
+  layout_exchange(lay, D, Q_CHAIN, nl, std::max(ml, nl));
   D.gath_blk = 0;
   if (D.d > 1) {
     const int64_t s = std::max<int64_t>(D.bc_local, 1) * 2;

@@ -171,9 +171,7 @@ capital_status_t peer_init(capital_ctx* ctx, peer_allgather_fn ag, void* user) {
   }
   int lo = 0, hi = 0;
   cudaDeviceGetStreamPriorityRange(&lo, &hi);
-  CAP_CUDA(cudaStreamCreateWithPriority(&P->push[0], cudaStreamNonBlocking, hi));
-  CAP_CUDA(cudaStreamCreateWithPriority(&P->push[1], cudaStreamNonBlocking, lo));
-  CAP_CUDA(cudaStreamCreateWithPriority(&P->push[2], cudaStreamNonBlocking, lo));
+  for (int q = 0; q < PEER_Q; q++) CAP_CUDA(cudaStreamCreateWithPriority(&P->push[q], cudaStreamNonBlocking, q == 0 ? hi : lo));
   return host_barrier(ctx);  // nobody proceeds (and possibly tears down) before every rank has mapped every control block
 }
 

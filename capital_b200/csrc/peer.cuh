@@ -17,14 +17,17 @@
 #include "common.cuh"
 
 constexpr int PEER_MAX_RANKS = 16;
-constexpr int PEER_Q = 3;                    // flag / push-stream classes: 0 = critical chain, 1 = deferred ("far") work, 2 = bulk pushes (node-entry operands)
-constexpr int PEER_QC = 2;                   // classes that run fused products (own compute stream, receive buffers, tile flags)
+constexpr int PEER_NFAR = 3;                 // deferred classes: one per recursion depth 0 .. 2 (a deeper node's deferred work is needed sooner
+                                             // than its ancestors' and must not queue behind it on one FIFO stream)
+constexpr int PEER_QC = 1 + PEER_NFAR;       // classes that run products (own compute stream, exchange buffers): 0 = critical chain, 1 .. = deferred
+constexpr int PEER_Q = PEER_QC + 1;          // flag / push-stream classes: the product classes + bulk pushes (node-entry operands)
 // control block layout (units of 8 bytes)
 constexpr size_t CTRL_PUSH = 0;                                   // [src][q]   "all I pushed to you on class q up to id v has landed"
 constexpr size_t CTRL_DONE = CTRL_PUSH + PEER_MAX_RANKS * PEER_Q; // [src][q]   "my fused product v on class q has retired"
 constexpr size_t CTRL_BAR = CTRL_DONE + PEER_MAX_RANKS * PEER_Q;  // [src]      world barrier epochs
 constexpr size_t CTRL_AR = CTRL_BAR + PEER_MAX_RANKS;             // [src]      small all-reduce epochs
-constexpr size_t CTRL_WORDS = 256;
+constexpr size_t CTRL_WORDS = 512;
+static_assert(CTRL_AR + PEER_MAX_RANKS <= CTRL_WORDS, "control block too small");
 
 typedef int (*peer_allgather_fn)(void* user, const void* send, void* recv, int64_t bytes_per_rank);
 
@@ -45,8 +48,8 @@ struct Peer {
   size_t arena_bytes = 0;
   char* peer_arena[PEER_MAX_RANKS] = {};
   cudaStream_t push[PEER_Q] = {};
-  unsigned long long push_id[PEER_Q] = {0, 0, 0};   // logical push events issued so far (same on every rank)
-  unsigned long long prod_seq[PEER_QC] = {0, 0};    // fused products issued so far
+  unsigned long long push_id[PEER_Q] = {};          // logical push events issued so far (same on every rank)
+  unsigned long long prod_seq[PEER_QC] = {};        // products with a depth exchange issued so far
   unsigned long long bar_epoch = 0, ar_epoch = 0;
   bool memops = true;   // flags through stream memory operations (no SM needed) instead of one-warp kernels [env CAPITAL_PEER_MEMOPS]
   // NCCL bootstrap (only when capital_comm_init was used)

@@ -110,7 +110,7 @@ capital_status_t capital_set_overlap(capital_ctx* ctx, int enabled);
 capital_status_t capital_profile_end(capital_ctx* ctx, double* kernel_ms, double* kernel_flops, int64_t* launches);
 /* Timeline of the schedule (profiling aid; the image has no nsys): between begin and end every launch of the library is bracketed by
  * CUDA events on its own stream.  end synchronizes the device and writes 8 doubles per launch: stream id (0 caller, 1 critical chain,
- * 2 deferred, 3..5 push streams, 6 copy-in, 7 copy-out), kind (1 big GEMM, 2 small GEMM, 3 cluster base case, 4 leaf, 5 flag wait,
+ * 2..4 deferred (recursion depth 0..2), 5..9 push streams, 10 copy-in, 11 copy-out), kind (1 big GEMM, 2 small GEMM, 3 cluster base case, 4 leaf, 5 flag wait,
  * 6 flag signal, 7 peer DMA, 8 layout kernel), start ms, end ms, three kind-specific numbers (GEMM: m, n, k), 0. */
 capital_status_t capital_timeline_begin(capital_ctx* ctx);
 capital_status_t capital_timeline_end(capital_ctx* ctx, double* out, int64_t cap_records, int64_t* n_records);

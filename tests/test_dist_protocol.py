@@ -17,7 +17,7 @@ import capital_b200 as cb
 from capital_b200 import _lib
 
 T_WAIT, T_SIGNAL, T_PRODUCT, T_EVREC, T_EVWAIT, T_DMA, T_KERNEL, T_READ, T_WRITE, T_MAT = range(1, 11)
-NSTREAM = 8
+NSTREAM = 12
 
 
 def trace(size, rank, c, n, ci, bcm):

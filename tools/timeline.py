@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import capital_b200 as cb
 
 KIND = {1: "gemm128", 2: "gemm64", 3: "basecase", 4: "leaf", 5: "wait", 6: "signal", 7: "dma", 8: "layout"}
-SID = {0: "user", 1: "chain", 2: "far", 3: "push0", 4: "push1", 5: "push2", 6: "copyin", 7: "copyout"}
+SID = {0: "user", 1: "chain", 2: "far0", 3: "far1", 4: "far2", 5: "push0", 6: "push1", 7: "push2", 8: "push3", 9: "pushB", 10: "copyin", 11: "copyout"}
 
 
 def main():
