@@ -14,8 +14,13 @@ OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "libcapital_b200.so")
 SOURCES = ["api.cu", "gemm_tn.cu", "leaf.cu", "layout.cu", "cholinv_local.cu", "dist.cu", "peer.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+# -dlcm=cg: plain global loads are cached in L2 only.  Buffers of the multi-GPU path are written by OTHER processes' copy engines and
+# kernels (peer DMA into mirror / gather slots, remote epilogue stores into exchange buffers and C replicas) and re-used every few
+# products; an L1 line that survives from the previous use would be read back stale (seen as a handful of wrong 128-byte lines when
+# kernels of two streams overlap, i.e. when "kernel boundaries" no longer flush an SM's L1).  L2 is the coherence point for those
+# writes.  The hot loops do not depend on L1 (TMA -> shared memory, or explicit __ldcg), and the layout kernels are streaming.
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-         "-Xcompiler", "-fvisibility=hidden", "-Xptxas", "-v"]
+         "-Xcompiler", "-fvisibility=hidden", "-Xptxas", "-v", "-Xptxas", "-dlcm=cg"]
 
 
 def _newer(a: str, b: str) -> bool:

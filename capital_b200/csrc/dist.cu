@@ -38,7 +38,7 @@ inline int rank_of(const capital_grid_t& g, int x, int y, int z) { return y * g.
 // ---- small kernels used only by the distributed schedules ---------------------------------------------------
 // gathered[(x' + d y')] = local block (s x s, ld lds) of slice rank x' + d y'  ->  dense (s d) x (s d) block, upper part
 // (util::block_to_cyclic_*, util.hpp:56-133)
-__global__ void blocks_to_dense_kernel(int s, int d, const double* __restrict__ gathered, long long lds, double* __restrict__ dense,
+__global__ void blocks_to_dense_kernel(int s, int d, const double* gathered, long long lds, double* dense,
                                        long long ldd) {
   const long long b = (long long)s * d, total = b * b;
   const long long blk = lds * s;
@@ -47,15 +47,15 @@ __global__ void blocks_to_dense_kernel(int s, int d, const double* __restrict__ 
     double v = 0.0;
     if (gy <= gx) {
       const int xo = (int)(gx % d), yo = (int)(gy % d);
-      v = gathered[(xo + (long long)d * yo) * blk + (gx / d) * lds + (gy / d)];
+      v = __ldcg(gathered + (xo + (long long)d * yo) * blk + (gx / d) * lds + (gy / d));  // L2 only: written by the slice members' DMA
     }
     dense[gx * ldd + gy] = v;
   }
 }
 // own cyclic part of three dense blocks at once: loc(j, i) = dense(y + d j, x + d i)   (util::cyclic_to_local, util.hpp:135-164)
-__global__ void dense_to_local3_kernel(int s, int d, int x, int y, const double* __restrict__ d0, const double* __restrict__ d1,
-                                       const double* __restrict__ d2, long long ldd, double* __restrict__ l0, double* __restrict__ l1,
-                                       double* __restrict__ l2, long long ldl) {
+__global__ void dense_to_local3_kernel(int s, int d, int x, int y, const double* d0, const double* d1,
+                                       const double* d2, long long ldd, double* l0, double* l1,
+                                       double* l2, long long ldl) {
   const long long total = (long long)s * s;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const long long i = idx / s, j = idx - i * s;
@@ -71,16 +71,16 @@ __global__ void dense_to_local3_kernel(int s, int d, int x, int y, const double*
 // once.  upper_only: entries with row > col0 + col are left alone (the producing GEMM only computed the upper tiles).
 struct PartialSrc { const double* p[GEMM_XPEERS_MAX + 1]; int n; };
 __global__ void __launch_bounds__(256) reduce_partials_kernel(long long rows, long long cols, PartialSrc src, long long ldp, double beta,
-                                                              double* __restrict__ C, long long ldc, int upper_only, long long col0) {
+                                                              double* C, long long ldc, int upper_only, long long col0) {
   const long long r2 = (rows + 1) / 2;  // row pairs: every buffer is 16-byte aligned with an even leading dimension
   for (long long c = blockIdx.y; c < cols; c += gridDim.y) {
     const long long rmax = upper_only ? min(rows, c + col0 + 1) : rows;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < r2; i += (long long)gridDim.x * blockDim.x) {
       const long long r = 2 * i;
       if (r >= rmax) break;
-      double2 v = __ldcs(reinterpret_cast<const double2*>(src.p[0] + c * ldp + r));
+      double2 v = __ldcg(reinterpret_cast<const double2*>(src.p[0] + c * ldp + r));  // L2 only: written by the partners' epilogues
       for (int l = 1; l < src.n; l++) {
-        const double2 w = __ldcs(reinterpret_cast<const double2*>(src.p[l] + c * ldp + r));
+        const double2 w = __ldcg(reinterpret_cast<const double2*>(src.p[l] + c * ldp + r));
         v.x += w.x; v.y += w.y;
       }
       double* cc = C + c * ldc + r;
@@ -171,6 +171,7 @@ struct Dist {
   int64_t far_min = 1024, side_min = 512;
   int64_t chunk_min = 4096;  // R12 / Rinv12 blocks at least this wide are produced and pushed in `chunks` column chunks [env CAPITAL_DIST_CHUNK_MIN]
   int chunks = 4;            // [env CAPITAL_DIST_CHUNKS]
+  bool bulk_class = true;    // node-entry pushes of A12 travel on their own push stream [env CAPITAL_DIST_BULK]
   // host-pointer callers: A arrives by column chunks on the copy-in stream; finished column ranges are packed and copied out while
   // the rest of the factorization runs
   std::vector<std::pair<int64_t, int>> in_chunks;  // (col_end, event)
@@ -333,6 +334,7 @@ capital_status_t dist_setup(Dist& D, capital_ctx* ctx, bool dry) {
   if (const char* e = getenv("CAPITAL_DIST_SIDE_MIN")) D.side_min = atoll(e);
   if (const char* e = getenv("CAPITAL_DIST_CHUNK_MIN")) D.chunk_min = atoll(e);
   if (const char* e = getenv("CAPITAL_DIST_CHUNKS")) D.chunks = atoi(e);
+  if (const char* e = getenv("CAPITAL_DIST_BULK")) D.bulk_class = atoi(e) != 0;
   if (ctx->no_overlap) D.two_stream = false;
   return CAPITAL_OK;
 }
@@ -670,8 +672,9 @@ capital_status_t invoke(Dist& D, int64_t o, int64_t s, bool complete, int pendin
   // left child computes (bulk class: it must not delay the chain's small pushes)
   Token tW12 = pendW12;
   if (pending < 0) {
-    CAP_TRY(need_cols(D, S_PUSH0 + Q_BULK, o + s));
-    CAP_TRY(push(D, Q_BULK, S_CHAIN, D.W, o, o + s1, s1, s2, ROLE_Y, &tW12));
+    const int qb = D.bulk_class ? Q_BULK : Q_CHAIN;
+    CAP_TRY(need_cols(D, S_PUSH0 + qb, o + s));
+    CAP_TRY(push(D, qb, S_CHAIN, D.W, o, o + s1, s1, s2, ROLE_Y, &tW12));
   }
   CAP_TRY(invoke(D, o, s1, true, -1, Token{}, depth + 1));
   if (D.stream_out && depth <= 3 && o + s == D.L) CAP_TRY(dist_left_done(D, o + s1, depth));  // right spine

@@ -9,7 +9,7 @@ namespace {
 
 constexpr int TP = 32;
 
-__global__ void transpose_kernel(int rows, int cols, const double* __restrict__ src, long long lds, double* __restrict__ dst,
+__global__ void transpose_kernel(int rows, int cols, const double* src, long long lds, double* dst,
                                  long long ldd, double scale) {
   __shared__ double tile[TP][TP + 1];
   const int r0 = blockIdx.x * TP, c0 = blockIdx.y * TP;
@@ -25,7 +25,7 @@ __global__ void transpose_kernel(int rows, int cols, const double* __restrict__ 
   }
 }
 
-__global__ void copy_kernel(long long rows, long long cols, const double* __restrict__ src, long long lds, double* __restrict__ dst,
+__global__ void copy_kernel(long long rows, long long cols, const double* src, long long lds, double* dst,
                             long long ldd) {
   const long long total = rows * cols;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -34,7 +34,7 @@ __global__ void copy_kernel(long long rows, long long cols, const double* __rest
   }
 }
 
-__global__ void zero_kernel(long long rows, long long cols, double* __restrict__ dst, long long ldd) {
+__global__ void zero_kernel(long long rows, long long cols, double* dst, long long ldd) {
   const long long total = rows * cols;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long c = i / rows, r = i - c * rows;
@@ -43,7 +43,7 @@ __global__ void zero_kernel(long long rows, long long cols, double* __restrict__
 }
 
 // one block per column chunk: column i of the packed triangle is contiguous (i+1 entries at i(i+1)/2)
-__global__ void pack_upper_kernel(long long c0, long long n, const double* __restrict__ src, long long lds, double* __restrict__ packed,
+__global__ void pack_upper_kernel(long long c0, long long n, const double* src, long long lds, double* packed,
                                   int zero_diag) {
   for (long long i = c0 + blockIdx.x; i < n; i += gridDim.x) {
     const double* s = src + i * lds;
@@ -54,7 +54,7 @@ __global__ void pack_upper_kernel(long long c0, long long n, const double* __res
 // rows [r0, min(r1, col + 1)) of columns [c0, c1) of a rect matrix -> their slots of the packed upper triangle.  `packed` may be
 // the device alias of a pinned host array: each column is one contiguous run of coalesced 8-byte stores, a handful of CTAs
 // keeps the PCIe link busy.
-__global__ void emit_block_packed_kernel(const double* __restrict__ src, long long lds, double* __restrict__ packed, long long r0, long long r1,
+__global__ void emit_block_packed_kernel(const double* src, long long lds, double* packed, long long r0, long long r1,
                                          long long c0, long long c1) {
   for (long long i = c0 + blockIdx.x; i < c1; i += gridDim.x) {
     const double* s = src + i * lds;
@@ -63,14 +63,14 @@ __global__ void emit_block_packed_kernel(const double* __restrict__ src, long lo
     for (long long j = r0 + threadIdx.x; j < re; j += blockDim.x) d[j] = s[j];
   }
 }
-__global__ void unpack_upper_kernel(long long n, const double* __restrict__ packed, double* __restrict__ dst, long long ldd) {
+__global__ void unpack_upper_kernel(long long n, const double* packed, double* dst, long long ldd) {
   for (long long i = blockIdx.x; i < n; i += gridDim.x) {
     const double* s = packed + i * (i + 1) / 2;
     double* d = dst + i * ldd;
     for (long long j = threadIdx.x; j < n; j += blockDim.x) d[j] = j <= i ? s[j] : 0.0;
   }
 }
-__global__ void triu_copy_kernel(long long n, const double* __restrict__ src, long long lds, double* __restrict__ dst, long long ldd,
+__global__ void triu_copy_kernel(long long n, const double* src, long long lds, double* dst, long long ldd,
                                  int zero_diag) {
   for (long long i = blockIdx.x; i < n; i += gridDim.x) {
     const double* s = src + i * lds;
@@ -87,7 +87,7 @@ __device__ __forceinline__ double drand48_first(unsigned long long seed) {
   return (double)x * (1.0 / 281474976710656.0);
 }
 
-__global__ void gen_symmetric_kernel(double* __restrict__ A, long long ld, long long lrows, long long lcols, long long n, int x, int y,
+__global__ void gen_symmetric_kernel(double* A, long long ld, long long lrows, long long lcols, long long n, int x, int y,
                                      int d, int diag_dom) {
   const long long total = lrows * lcols;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -115,7 +115,7 @@ __device__ __forceinline__ void lcg_pow(unsigned long long t, unsigned long long
     t >>= 1;
   }
 }
-__global__ void gen_random_kernel(double* __restrict__ Aout, long long ld, long long lrows, long long lcols, long long pad_rows,
+__global__ void gen_random_kernel(double* Aout, long long ld, long long lrows, long long lcols, long long pad_rows,
                                   long long pad_cols, long long key) {
   const unsigned long long m48 = (1ULL << 48) - 1;
   const unsigned long long x0 = (((unsigned long long)key & 0xFFFFFFFFULL) << 16) | 0x330EULL;
@@ -134,8 +134,8 @@ __global__ void gen_random_kernel(double* __restrict__ Aout, long long ld, long 
 }
 
 // upper_mode: 0 = all entries, 1 = only entries whose GLOBAL position satisfies row <= col
-__global__ void sumsq_kernel(long long rows, long long cols, const double* __restrict__ a, long long ld, int upper_mode, int x, int y,
-                             int d, double* __restrict__ out) {
+__global__ void sumsq_kernel(long long rows, long long cols, const double* a, long long ld, int upper_mode, int x, int y,
+                             int d, double* out) {
   double s = 0.0;
   const long long total = rows * cols;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -155,12 +155,12 @@ __global__ void sumsq_kernel(long long rows, long long cols, const double* __res
   }
 }
 
-__global__ void sub_identity_kernel(long long n, double* __restrict__ a, long long ld) {
+__global__ void sub_identity_kernel(long long n, double* a, long long ld) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) a[i * ld + i] -= 1.0;
 }
 
 // zero the band |row - col| <= hw of an n x n matrix
-__global__ void zero_band_kernel(long long n, long long hw, double* __restrict__ a, long long ld) {
+__global__ void zero_band_kernel(long long n, long long hw, double* a, long long ld) {
   const long long w = 2 * hw + 1, total = n * w;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const long long c = idx / w, r = c - hw + (idx - c * w);

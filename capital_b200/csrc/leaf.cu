@@ -114,13 +114,13 @@ __device__ void leaf_factor_invert(int nb, double* __restrict__ a, double* __res
   }
 }
 
-__device__ __forceinline__ void leaf_load(int nb, const double* __restrict__ W, long long ldw, double* __restrict__ a) {
+__device__ __forceinline__ void leaf_load(int nb, const double* W, long long ldw, double* __restrict__ a) {
   for (int idx = threadIdx.x; idx < nb * nb; idx += 256) {
     const int i = idx % nb, j = idx / nb;
     a[i + j * LD] = (i <= j) ? __ldcg(W + i + (long long)j * ldw) : 0.0;
   }
 }
-__device__ __forceinline__ void leaf_store(int nb, const double* __restrict__ a, const double* __restrict__ r, double* __restrict__ R,
+__device__ __forceinline__ void leaf_store(int nb, const double* a, const double* r, double* __restrict__ R,
                                            long long ldr, double* __restrict__ Ri, long long ldri, double* __restrict__ RiT,
                                            long long ldrit) {
   for (int idx = threadIdx.x; idx < nb * nb; idx += 256) {
@@ -137,7 +137,7 @@ __device__ __forceinline__ void leaf_store(int nb, const double* __restrict__ a,
 }
 
 __global__ void __launch_bounds__(256, 1)
-    leaf_kernel(int nb, const double* __restrict__ W, long long ldw, double* __restrict__ R, long long ldr, double* __restrict__ Ri,
+    leaf_kernel(int nb, const double* W, long long ldw, double* __restrict__ R, long long ldr, double* __restrict__ Ri,
                 long long ldri, double* __restrict__ RiT, long long ldrit, int* __restrict__ info) {
   extern __shared__ double sm[];
   double* a = sm;
@@ -154,7 +154,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 // copy a 64 (k) x 64 (cols) global block (k contiguous, 16-byte aligned, even ld) into a padded tile: dst[col * TLD + k]
-__device__ __forceinline__ void tile_load(double* __restrict__ dst, const double* __restrict__ src, long long ld) {
+__device__ __forceinline__ void tile_load(double* __restrict__ dst, const double* src, long long ld) {
   const int k2 = (threadIdx.x & 31) * 2, c0 = threadIdx.x >> 5;
   double2 v[8];
 #pragma unroll
@@ -163,7 +163,7 @@ __device__ __forceinline__ void tile_load(double* __restrict__ dst, const double
   for (int r = 0; r < 8; r++) *reinterpret_cast<double2*>(dst + (c0 + 8 * r) * TLD + k2) = v[r];
 }
 // acc += As^T Bs for the 64x64 tile; warp w owns rows (w&1)*32.., cols (w>>1)*16..; As/Bs: [row][k] padded tiles.
-__device__ __forceinline__ void tile_mma(double (&acc)[4][2][2], const double* __restrict__ As, const double* __restrict__ Bs) {
+__device__ __forceinline__ void tile_mma(double (&acc)[4][2][2], const double* As, const double* Bs) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
   const double* ap = As + ((w & 1) * 32 + g) * TLD + q;
   const double* bp = Bs + ((w >> 1) * 16 + g) * TLD + q;
@@ -210,7 +210,7 @@ __device__ __forceinline__ void acc_to_smem_rowmajor(const double (&acc)[4][2][2
 }
 // global(64 x 64 block, column-major) = [beta * global +] sC ([col][row]) with 16-byte coalesced accesses
 template <bool ACCUM>
-__device__ __forceinline__ void tile_store(double* __restrict__ dst, long long ld, const double* __restrict__ sC) {
+__device__ __forceinline__ void tile_store(double* __restrict__ dst, long long ld, const double* sC) {
   const int r2 = (threadIdx.x & 31) * 2, c0 = threadIdx.x >> 5;
 #pragma unroll
   for (int r = 0; r < 8; r++) {
@@ -222,7 +222,7 @@ __device__ __forceinline__ void tile_store(double* __restrict__ dst, long long l
   }
 }
 // transposed store: global(col-block rows, row-block cols) = sC^T, reading sC ([row][col] order) so that accesses stay coalesced
-__device__ __forceinline__ void tile_store_from_rowmajor(double* __restrict__ dst, long long ld, const double* __restrict__ sCr) {
+__device__ __forceinline__ void tile_store_from_rowmajor(double* __restrict__ dst, long long ld, const double* sCr) {
   // sCr[row * TLD + col] holds value(row, col); we write dst(col, row) = value(row, col): dst column index = row
   const int c2 = (threadIdx.x & 31) * 2, r0 = threadIdx.x >> 5;
 #pragma unroll
@@ -364,7 +364,7 @@ __device__ __forceinline__ void warp_potrf_trtri_32(double (&c)[32], double* __r
 
 // acc(8 x 16 per warp) += A^T B over k in [k0, k0 + 32) for the 32 x 32 output block at (rows ar.., cols bc..) of the tiles
 // As ([row][k]) and Bs ([col][k]); warp w owns fragment row (w & 3) and fragment columns 2 (w >> 2) + {0, 1}.
-__device__ __forceinline__ void mma32(double (&acc)[2][2], const double* __restrict__ As, int ar, const double* __restrict__ Bs, int bc, int k0) {
+__device__ __forceinline__ void mma32(double (&acc)[2][2], const double* As, int ar, const double* Bs, int bc, int k0) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
   const double* ap = As + (ar + (w & 3) * 8 + g) * TLD + k0 + q;
   const double* bp = Bs + (bc + (w >> 2) * 16 + g) * TLD + k0 + q;

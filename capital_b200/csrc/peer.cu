@@ -81,12 +81,12 @@ __global__ void wait_kernel(FlagList fl, int* err) {
 }
 // dst_r[slot(me)][i] = src[i] on every rank r (own copy included): blockIdx.y = destination rank
 struct ArDst { double* p[PEER_MAX_RANKS]; };
-__global__ void ar_scatter_kernel(const double* __restrict__ src, long long count, ArDst dst) {
+__global__ void ar_scatter_kernel(const double* src, long long count, ArDst dst) {
   double* d = dst.p[blockIdx.y];
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) d[i] = src[i];
   __threadfence_system();
 }
-__global__ void ar_sum_kernel(double* __restrict__ buf, long long count, const double* __restrict__ slots, int size) {
+__global__ void ar_sum_kernel(double* buf, long long count, const double* slots, int size) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
     double s = __ldcg(slots + i);
     for (int r = 1; r < size; r++) s += __ldcg(slots + (long long)r * count + i);  // rank order: the same bits on every rank
