@@ -322,6 +322,39 @@ def ours(args):
     ms_step = reduce_max(ms) / args.steps
     value = n ** 3 / 3 / (ms_step * 1e-3) / 1e12
     residual = cb.cholinv.residual(A, pack, topo)
+    # optional: one more step with CUDA events around every launch (the image has no nsys), summarised into the line and saved per rank
+    timeline = None
+    if os.environ.get("CAPITAL_BENCH_TIMELINE"):
+        try:
+            cb.cholinv.factor(A, pack, topo)
+            barrier()
+            ctx.timeline_begin()
+            cb.cholinv.factor(A, pack, topo)
+            tl = ctx.timeline_end()
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            np.save(os.path.join(ROOT, "gpurun_out", f"timeline_n{world}_r{rank}.npy"), tl)
+
+            def union(iv):
+                iv = sorted(iv)
+                tot, (cs, ce) = 0.0, iv[0]
+                for a, b in iv[1:]:
+                    if a > ce:
+                        tot += ce - cs; cs, ce = a, b
+                    else:
+                        ce = max(ce, b)
+                return tot + ce - cs
+            big = tl[tl[:, 1] == 1]
+            ch = tl[tl[:, 0] == 1]
+            w = ch[ch[:, 1] == 5]
+            chs = ch[np.argsort(ch[:, 2])]
+            gaps = chs[1:, 2] - chs[:-1, 3]
+            timeline = {"span_ms": float(tl[:, 3].max() - tl[:, 2].min()), "launches": int(len(tl)),
+                        "big_gemm_union_ms": float(union([(a, b) for a, b in big[:, 2:4]])) if len(big) else 0.0,
+                        "chain_busy_ms": float((ch[:, 3] - ch[:, 2]).sum()), "chain_flag_wait_ms": float((w[:, 3] - w[:, 2]).sum()) if len(w) else 0.0,
+                        "chain_gaps_over_1ms": [float(g) for g in np.sort(gaps[gaps > 1.0])[-6:]],
+                        "note": "rank 0, one extra step with events around every launch (slower than the timed steps)"}
+        except Exception as ex:  # noqa
+            timeline = {"error": repr(ex)[:200]}
 
     # ---- end to end: pinned host buffers through the same public call ----
     e2e = None
@@ -404,6 +437,8 @@ def ours(args):
                          "peak_source": peak_src},
             "e2e": e2e, "gpu_launches": int(cnt.kernel_launches), "clocks": summarize_clocks(samples),
         }
+        if timeline is not None:
+            out["timeline"] = timeline
         if parity is not None:
             out["parity"] = parity
         if strong is not None:
