@@ -260,8 +260,17 @@ struct Dist {
       return CAPITAL_OK;
     }
     const int tli = ctx->tl_begin(strm(sid), 7, (double)rows, (double)cols, (double)dst_rank);
-    if (rows == lds && rows == ldd) CAP_CUDA(cudaMemcpyAsync(dst, src, (size_t)rows * cols * 8, cudaMemcpyDefault, strm(sid)));
-    else CAP_CUDA(cudaMemcpy2DAsync(dst, (size_t)ldd * 8, src, (size_t)lds * 8, (size_t)rows * 8, (size_t)cols, cudaMemcpyDefault, strm(sid)));
+    // in pieces of at most 512 MiB (whole columns): a single peer copy of exactly 2 GiB -- the L x L operand of the n = 32768
+    // validator on the 2 x 2 x 2 grid -- was observed to let the flag that follows it overtake the tail of the data
+    // (profiles/r02c_coherence_bug_notes.md); smaller pieces also let several copy engines work on one push
+    const int64_t cpp = std::max<int64_t>(1, ((int64_t)512 << 20) / (rows * 8));
+    for (int64_t c0 = 0; c0 < cols; c0 += cpp) {
+      const int64_t nc = std::min(cpp, cols - c0);
+      double* dp = dst + c0 * ldd;
+      const double* sp = src + c0 * lds;
+      if (rows == lds && rows == ldd) CAP_CUDA(cudaMemcpyAsync(dp, sp, (size_t)rows * nc * 8, cudaMemcpyDefault, strm(sid)));
+      else CAP_CUDA(cudaMemcpy2DAsync(dp, (size_t)ldd * 8, sp, (size_t)lds * 8, (size_t)rows * 8, (size_t)nc, cudaMemcpyDefault, strm(sid)));
+    }
     ctx->tl_end(strm(sid), tli);
     return CAPITAL_OK;
   }

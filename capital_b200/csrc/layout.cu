@@ -4,6 +4,7 @@
 // validators' Frobenius reductions (util.hpp:25-53).  All kernels are coalesced along the contiguous
 // (row) index and sized in multiples of the SM count where the extent allows.
 #include "common.cuh"
+#include <algorithm>
 
 namespace {
 
@@ -198,7 +199,9 @@ capital_status_t copy_block(capital_ctx* ctx, cudaStream_t st, int64_t rows, int
                             int64_t ldd) {
   if (rows <= 0 || cols <= 0) return CAPITAL_OK;
   if (lds == rows && ldd == rows) {
-    CAP_CUDA(cudaMemcpyAsync(dst, src, (size_t)rows * cols * 8, cudaMemcpyDeviceToDevice, st));
+    const size_t total = (size_t)rows * cols * 8, piece = (size_t)1 << 30;  // pieces of at most 1 GiB (see dist.cu: dma2d)
+    for (size_t off = 0; off < total; off += piece)
+      CAP_CUDA(cudaMemcpyAsync((char*)dst + off, (const char*)src + off, std::min(piece, total - off), cudaMemcpyDeviceToDevice, st));
     return CAPITAL_OK;
   }
   const int tli = ctx->tl_begin(st, 8, 2, (double)rows, (double)cols);
