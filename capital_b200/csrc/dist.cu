@@ -70,6 +70,11 @@ __global__ void dense_to_local3_kernel(int s, int d, int x, int y, const double*
 // every layer (identical bits in every replica).  One streaming pass: every partial is read once, C is read (beta != 0) and written
 // once.  upper_only: entries with row > col0 + col are left alone (the producing GEMM only computed the upper tiles).
 struct PartialSrc { const double* p[GEMM_XPEERS_MAX + 1]; int n; };
+__device__ __forceinline__ double2 ld_sys(const double* p) {
+  double2 v;
+  asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+  return v;
+}
 __global__ void __launch_bounds__(256) reduce_partials_kernel(long long rows, long long cols, PartialSrc src, long long ldp, double beta,
                                                               double* C, long long ldc, int upper_only, long long col0) {
   const long long r2 = (rows + 1) / 2;  // row pairs: every buffer is 16-byte aligned with an even leading dimension
@@ -78,9 +83,10 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(long long rows, lo
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < r2; i += (long long)gridDim.x * blockDim.x) {
       const long long r = 2 * i;
       if (r >= rmax) break;
-      double2 v = __ldcg(reinterpret_cast<const double2*>(src.p[0] + c * ldp + r));  // L2 only: written by the partners' epilogues
+      // system-scope loads: all but one of the partials were stored by OTHER GPUs' epilogues over NVLink
+      double2 v = ld_sys(src.p[0] + c * ldp + r);
       for (int l = 1; l < src.n; l++) {
-        const double2 w = __ldcg(reinterpret_cast<const double2*>(src.p[l] + c * ldp + r));
+        const double2 w = ld_sys(src.p[l] + c * ldp + r);
         v.x += w.x; v.y += w.y;
       }
       double* cc = C + c * ldc + r;
@@ -160,8 +166,9 @@ struct Dist {
   DMat W, R, Ri, RiT;
   // partial products of the k-split exchange, per stream class: my own partial, and two alternating sets of receive buffers (one
   // per other layer) that the partners' GEMM epilogues store into
-  double* pown[PEER_QC] = {};
-  double* precv[PEER_QC][2] = {};
+  double* pown[PEER_QC][3] = {};
+  double* precv[PEER_QC][3] = {};
+  int nsets[PEER_QC] = {};            // rotating buffer sets of the class (3 on the chain: chunked products are software-pipelined)
   size_t precv_stride[PEER_QC] = {};  // doubles per partial buffer of the class
   double* gath[2] = {nullptr, nullptr};
   int64_t gath_blk = 0;
@@ -380,10 +387,14 @@ void layout_mat(Layout& lay, const Dist& D, DMat& M, int64_t ld, int64_t cols, i
 // partial-product buffers of the k-split exchange of one stream class, for products of up to `elems` output elements
 void layout_exchange(Layout& lay, Dist& D, int q, int64_t m, int64_t n) {
   D.precv_stride[q] = 0;
+  D.nsets[q] = 0;
   if (D.xmode != 1) return;
+  D.nsets[q] = q == Q_CHAIN ? 3 : 2;
   D.precv_stride[q] = (size_t)round_up((int64_t)((size_t)packed_ld(m) * n), 128);
-  D.pown[q] = lay.take(D.precv_stride[q]);
-  for (int b = 0; b < 2; b++) D.precv[q][b] = lay.take(D.precv_stride[q] * (size_t)(D.c - 1));
+  for (int b = 0; b < D.nsets[q]; b++) {
+    D.pown[q][b] = lay.take(D.precv_stride[q]);
+    D.precv[q][b] = lay.take(D.precv_stride[q] * (size_t)(D.c - 1));
+  }
 }
 
 // ---- push: a finished block goes to everybody who will read it ----------------------------------------------------------
@@ -435,11 +446,36 @@ inline void add_waits(const Dist& D, std::vector<Flag>& w, int s, const Token* t
 // globals; local windows: X: k x m, Y: k x n, C: m x n).  The blocks actually multiplied are the ones owned by the class sources;
 // the result is complete in EVERY replica when the call's work has drained from the class stream.  `noff`: column position of the
 // window inside the full operand (column-chunked products keep the triangular k ranges and the upper mask right).
-capital_status_t product(Dist& D, int q, int64_t m, int64_t n, int64_t k, double alpha, Win X, Win Y, double beta, Win C, int flags,
-                         const Token* farX = nullptr, const Token* farY = nullptr, int noff = 0) {
+//
+// Two halves.  product_issue: wait for the operands, run the GEMM (storing this layer's partial into every layer's buffers when the
+// contraction is split over the layers), tell the partners.  product_finish: wait for the partners, add the partials up.  Chunked
+// products issue chunk j + 1 before finishing chunk j, so the (few-percent) skew between the two layers' GEMMs hides behind a GEMM.
+struct PendingProduct {
+  bool active = false;
+  int q = 0;
+  unsigned long long seq = 0;
+  int64_t m = 0, n = 0, ldp = 0, ldc = 0;
+  double beta = 0.0;
+  double* Cown = nullptr;
+  int upper = 0, noff = 0;
+  PartialSrc src{};
+};
+inline std::vector<Flag> partner_flags(const Dist& D, size_t base, int q, unsigned long long v, bool mine) {
+  std::vector<Flag> f;
+  for (int l = 0; l < D.c; l++) {
+    if (l == D.g.z) continue;
+    const int partner = rank_of(D.g, D.g.x, D.g.y, l);
+    if (mine) f.push_back({partner, base + (size_t)D.me * PEER_Q + q, v});   // my flag in the partner's block
+    else f.push_back({D.me, base + (size_t)partner * PEER_Q + q, v});         // the partner's flag in mine
+  }
+  return f;
+}
+capital_status_t product_issue(Dist& D, int q, int64_t m, int64_t n, int64_t k, double alpha, Win X, Win Y, double beta, Win C, int flags,
+                               const Token* farX, const Token* farY, int noff, PendingProduct* pd) {
   capital_ctx* ctx = D.ctx;
   Peer* P = D.P;
   const int sid = D.cstream(q);
+  pd->active = false;
   if (m <= 0 || n <= 0 || k <= 0) return CAPITAL_OK;
   GemmOperands ops;
   ops.ncls = D.nk; ops.lda = X.M->ld; ops.ldb = Y.M->ld;
@@ -465,20 +501,9 @@ capital_status_t product(Dist& D, int q, int64_t m, int64_t n, int64_t k, double
     } else CAP_TRY(gemm_tn_x(ctx, D.strm(sid), m, n, k, alpha, ops, beta, Cown, ldc, flags, 0, noff, nullptr));
     return CAPITAL_OK;
   }
-  // Flags of the depth handshake: ready(p) = 2 seq - 1 ("nothing I enqueued before product p still reads its C window"), done(p) =
-  // 2 seq ("my kernel has retired: everything it stored, here and in the partners' memory, is performed").
+  // Flags of the depth handshake (CTRL_DONE): ready(p) = 2 seq - 1 ("nothing I enqueued before product p still reads its C
+  // window"), done(p) = 2 seq ("my kernel has retired: everything it stored, here and in the partners' memory, is performed").
   const unsigned long long seq = ++P->prod_seq[q];
-  auto handshake = [&](unsigned long long v) -> capital_status_t {
-    std::vector<Flag> s, ww;
-    for (int l = 0; l < D.c; l++) {
-      if (l == D.g.z) continue;
-      const int partner = rank_of(D.g, D.g.x, D.g.y, l);
-      s.push_back({partner, CTRL_DONE + (size_t)D.me * PEER_Q + q, v});
-      ww.push_back({D.me, CTRL_DONE + (size_t)partner * PEER_Q + q, v});
-    }
-    CAP_TRY(D.signal_flags(sid, s));
-    return D.wait_flags(sid, ww);
-  };
   GemmXDev x{};
   x.mode = D.xmode; x.c = D.c; x.z = D.g.z;
   if (D.xmode == 2) {
@@ -488,72 +513,108 @@ capital_status_t product(Dist& D, int q, int64_t m, int64_t n, int64_t k, double
       if (l == D.g.z) continue;
       x.Cpeer[l < D.g.z ? l : l - 1] = peer_ptr(P, rank_of(D.g, D.g.x, D.g.y, l), Cown);
     }
-    CAP_TRY(handshake(2 * seq - 1));
+    CAP_TRY(D.signal_flags(sid, partner_flags(D, CTRL_DONE, q, 2 * seq - 1, true)));
+    CAP_TRY(D.wait_flags(sid, partner_flags(D, CTRL_DONE, q, 2 * seq - 1, false)));
     if (D.dry) {
       D.rd(sid, ops.A[0], ops.lda, k, m); D.rd(sid, ops.B[0], ops.ldb, k, n);
-      const int64_t group = (int64_t)(seq * 4 + q + 1);
+      const int64_t group = (int64_t)(seq * 8 + q + 1);
       D.wr(sid, D.me, Cown, ldc, m, n, group);
       for (int l = 0; l < D.c; l++)
         if (l != D.g.z) D.wr(sid, rank_of(D.g, D.g.x, D.g.y, l), Cown, ldc, m, n, group);
       D.rec(T_PRODUCT, sid, q, (int64_t)seq, 2);
     } else CAP_TRY(gemm_tn_x(ctx, D.strm(sid), m, n, k, alpha, ops, beta, Cown, ldc, flags, 0, noff, &x));
-    return handshake(2 * seq);
+    CAP_TRY(D.signal_flags(sid, partner_flags(D, CTRL_DONE, q, 2 * seq, true)));
+    return D.wait_flags(sid, partner_flags(D, CTRL_DONE, q, 2 * seq, false));
   }
   // k split (c == d): the GEMM stores this layer's partial product into its own buffer and, over NVLink, into the receive buffer
-  // every other layer keeps for it (alternating sets: a partner may already run product p + 1 while this layer still adds up p);
-  // one handshake later every layer holds all c partials and adds them in layer order.
+  // every other layer keeps for it.  The buffers rotate over D.nsets[q] sets; a set is written again only after every layer has
+  // said (CTRL_RED) that it has added up the product that used it last.
+  const int nsets = D.nsets[q];
   const int64_t ldp = packed_ld(m);
   const size_t stride = D.precv_stride[q];
   if ((size_t)ldp * (size_t)n > stride) {
     ctx->set_error("distributed product: exchange buffers too small for a " + std::to_string(m) + " x " + std::to_string(n) + " product");
     return CAPITAL_ERR_UNSUPPORTED;
   }
-  double* recv_set = D.precv[q][seq & 1];
-  PartialSrc src{};
-  src.n = D.c;
+  const int set = (int)(seq % nsets);
+  double* own_set = D.pown[q][set];
+  double* recv_set = D.precv[q][set];
+  pd->src = PartialSrc{};
+  pd->src.n = D.c;
   for (int l = 0; l < D.c; l++) {
-    if (l == D.g.z) { src.p[l] = D.pown[q]; continue; }
+    if (l == D.g.z) { pd->src.p[l] = own_set; continue; }
     const int oi = l < D.g.z ? l : l - 1;          // index of layer l among MY others
     const int mi = D.g.z < l ? D.g.z : D.g.z - 1;  // index of my layer among layer l's others
     x.Cpeer[oi] = peer_ptr(P, rank_of(D.g, D.g.x, D.g.y, l), recv_set + (size_t)mi * stride);
-    src.p[l] = recv_set + (size_t)oi * stride;
+    pd->src.p[l] = recv_set + (size_t)oi * stride;
   }
+  if (seq > (unsigned long long)nsets) CAP_TRY(D.wait_flags(sid, partner_flags(D, CTRL_RED, q, seq - nsets, false)));
   if (D.dry) {
     for (int j = 0; j < D.nk; j++) { D.rd(sid, ops.A[j], ops.lda, k, m); D.rd(sid, ops.B[j], ops.ldb, k, n); }
-    D.wr(sid, D.me, D.pown[q], ldp, m, n);
+    D.wr(sid, D.me, own_set, ldp, m, n);
     for (int l = 0; l < D.c; l++)
       if (l != D.g.z) D.wr(sid, rank_of(D.g, D.g.x, D.g.y, l), recv_set + (size_t)(D.g.z < l ? D.g.z : D.g.z - 1) * stride, ldp, m, n);
     D.rec(T_PRODUCT, sid, q, (int64_t)seq, 1);
-  } else CAP_TRY(gemm_tn_x(ctx, D.strm(sid), m, n, k, alpha, ops, 0.0, D.pown[q], ldp, flags, 0, noff, &x));
-  CAP_TRY(handshake(2 * seq));
+  } else CAP_TRY(gemm_tn_x(ctx, D.strm(sid), m, n, k, alpha, ops, 0.0, own_set, ldp, flags, 0, noff, &x));
+  CAP_TRY(D.signal_flags(sid, partner_flags(D, CTRL_DONE, q, 2 * seq, true)));
+  pd->active = true; pd->q = q; pd->seq = seq; pd->m = m; pd->n = n; pd->ldp = ldp; pd->ldc = ldc; pd->beta = beta; pd->Cown = Cown;
+  pd->upper = (flags & CAPITAL_GEMM_C_UPPER) ? 1 : 0; pd->noff = noff;
+  return CAPITAL_OK;
+}
+capital_status_t product_finish(Dist& D, PendingProduct* pd) {
+  if (!pd->active) return CAPITAL_OK;
+  capital_ctx* ctx = D.ctx;
+  const int q = pd->q, sid = D.cstream(q);
+  pd->active = false;
+  CAP_TRY(D.wait_flags(sid, partner_flags(D, CTRL_DONE, q, 2 * pd->seq, false)));
   if (D.dry) {
-    for (int l = 0; l < D.c; l++) D.rd(sid, src.p[l], ldp, m, n);
-    D.wr(sid, D.me, Cown, ldc, m, n);
+    for (int l = 0; l < D.c; l++) D.rd(sid, pd->src.p[l], pd->ldp, pd->m, pd->n);
+    D.wr(sid, D.me, pd->Cown, pd->ldc, pd->m, pd->n);
     D.rec(T_KERNEL, sid);
   } else {
-    const int tli = ctx->tl_begin(D.strm(sid), 8, 4, (double)m, (double)n);
-    const long long r2 = (m + 1) / 2;
-    dim3 grid((unsigned)std::min<long long>(std::max<long long>(1, (r2 + 255) / 256), 64), (unsigned)std::min<int64_t>(n, 4 * (int64_t)ctx->num_sms));
-    reduce_partials_kernel<<<grid, 256, 0, D.strm(sid)>>>(m, n, src, ldp, beta, Cown, ldc, (flags & CAPITAL_GEMM_C_UPPER) ? 1 : 0, noff);
+    const int tli = ctx->tl_begin(D.strm(sid), 8, 4, (double)pd->m, (double)pd->n);
+    const long long r2 = (pd->m + 1) / 2;
+    dim3 grid((unsigned)std::min<long long>(std::max<long long>(1, (r2 + 255) / 256), 64), (unsigned)std::min<int64_t>(pd->n, 4 * (int64_t)ctx->num_sms));
+    reduce_partials_kernel<<<grid, 256, 0, D.strm(sid)>>>(pd->m, pd->n, pd->src, pd->ldp, pd->beta, pd->Cown, pd->ldc, pd->upper, pd->noff);
     ctx->tl_end(D.strm(sid), tli);
     ctx->counters.kernel_launches++;
     CAP_CUDA(cudaGetLastError());
   }
-  return CAPITAL_OK;
+  return D.signal_flags(sid, partner_flags(D, CTRL_RED, q, pd->seq, true));
+}
+capital_status_t product(Dist& D, int q, int64_t m, int64_t n, int64_t k, double alpha, Win X, Win Y, double beta, Win C, int flags,
+                         const Token* farX = nullptr, const Token* farY = nullptr, int noff = 0) {
+  PendingProduct pd;
+  CAP_TRY(product_issue(D, q, m, n, k, alpha, X, Y, beta, C, flags, farX, farY, noff, &pd));
+  return product_finish(D, &pd);
 }
 
 // The same product issued in `nch` column chunks of the output, each pushed to its consumers (roles != 0) as soon as it is complete:
-// the transfer of chunk j hides behind the GEMM of chunk j + 1 and only the last chunk's travel time stays exposed.
+// the transfer of chunk j hides behind the GEMM of chunk j + 1, the partners' skew of chunk j behind it too, and only the last
+// chunk's handshake and travel time stay exposed.
 capital_status_t product_pushed(Dist& D, int q, int64_t m, int64_t n, int64_t k, double alpha, Win X, Win Y, double beta, Win C, int flags,
                                 const Token* farX, const Token* farY, int roles, Token* last, int nch) {
   if (nch < 1) nch = 1;
   const int64_t cw = round_up(ceil_div(n, nch), 128);
+  PendingProduct prev;
+  int64_t prev_c0 = 0, prev_nc = 0;
+  auto finish_prev = [&]() -> capital_status_t {
+    if (prev_nc == 0) return CAPITAL_OK;
+    CAP_TRY(product_finish(D, &prev));
+    if (roles) CAP_TRY(push(D, q, D.cstream(q), *C.M, C.r0, C.c0 + prev_c0, m, prev_nc, roles, last));
+    prev_nc = 0;
+    return CAPITAL_OK;
+  };
+  const bool pipelined = D.xmode == 1 && D.nsets[q] >= 3;
   for (int64_t c0 = 0; c0 < n; c0 += cw) {
     const int64_t nc = std::min(cw, n - c0);
-    CAP_TRY(product(D, q, m, nc, k, alpha, X, Win{Y.M, Y.r0, Y.c0 + c0}, beta, Win{C.M, C.r0, C.c0 + c0}, flags, farX, farY, (int)c0));
-    if (roles) CAP_TRY(push(D, q, D.cstream(q), *C.M, C.r0, C.c0 + c0, m, nc, roles, last));
+    PendingProduct cur;
+    if (!pipelined) CAP_TRY(finish_prev());
+    CAP_TRY(product_issue(D, q, m, nc, k, alpha, X, Win{Y.M, Y.r0, Y.c0 + c0}, beta, Win{C.M, C.r0, C.c0 + c0}, flags, farX, farY, (int)c0, &cur));
+    CAP_TRY(finish_prev());
+    prev = cur; prev_c0 = c0; prev_nc = nc;
   }
-  return CAPITAL_OK;
+  return finish_prev();
 }
 
 // dst (local cols x rows block) = [rows x cols window of the transpose partner's `Src`]^T   (util::transpose, util.hpp:232-247,

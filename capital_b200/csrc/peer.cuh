@@ -26,8 +26,9 @@ constexpr size_t CTRL_PUSH = 0;                                   // [src][q]   
 constexpr size_t CTRL_DONE = CTRL_PUSH + PEER_MAX_RANKS * PEER_Q; // [src][q]   "my fused product v on class q has retired"
 constexpr size_t CTRL_BAR = CTRL_DONE + PEER_MAX_RANKS * PEER_Q;  // [src]      world barrier epochs
 constexpr size_t CTRL_AR = CTRL_BAR + PEER_MAX_RANKS;             // [src]      small all-reduce epochs
+constexpr size_t CTRL_RED = CTRL_AR + PEER_MAX_RANKS;             // [src][q]   "I have added up the partials of product v of class q"
 constexpr size_t CTRL_WORDS = 512;
-static_assert(CTRL_AR + PEER_MAX_RANKS <= CTRL_WORDS, "control block too small");
+static_assert(CTRL_RED + PEER_MAX_RANKS * PEER_Q <= CTRL_WORDS, "control block too small");
 
 typedef int (*peer_allgather_fn)(void* user, const void* send, void* recv, int64_t bytes_per_rank);
 
