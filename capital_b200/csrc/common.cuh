@@ -146,6 +146,8 @@ capital_status_t gemm_tn_chunked(capital_ctx* ctx, cudaStream_t st, int64_t m, i
                                  int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags, int64_t kc);
 capital_status_t gemm_tn_splitk(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
                                 int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int flags);
+capital_status_t gemm_tn_t(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
+                           const double* B, int64_t ldb, double* C, int64_t ldc, double* Ct, int64_t ldct, int flags);
 
 // ---- layout.cu --------------------------------------------------------------------------------
 capital_status_t transpose_block(capital_ctx* ctx, cudaStream_t st, int64_t rows, int64_t cols, const double* src,

@@ -179,6 +179,8 @@ struct Dist {
   int64_t chunk_min = 4096;  // R12 / Rinv12 blocks at least this wide are produced and pushed in `chunks` column chunks [env CAPITAL_DIST_CHUNK_MIN]
   int chunks = 4;            // [env CAPITAL_DIST_CHUNKS]
   bool bulk_class = true;    // node-entry pushes of A12 travel on their own push stream [env CAPITAL_DIST_BULK]
+  bool pipeline = false;     // chunked products issue chunk j + 1 before adding up chunk j (hides the layers' skew) [env CAPITAL_DIST_PIPELINE];
+                             // protocol-checked, but off until it has a clean multi-GPU soak (profiles/r02c_coherence_bug_notes.md)
   // host-pointer callers: A arrives by column chunks on the copy-in stream; finished column ranges are packed and copied out while
   // the rest of the factorization runs
   std::vector<std::pair<int64_t, int>> in_chunks;  // (col_end, event)
@@ -351,6 +353,7 @@ capital_status_t dist_setup(Dist& D, capital_ctx* ctx, bool dry) {
   if (const char* e = getenv("CAPITAL_DIST_CHUNK_MIN")) D.chunk_min = atoll(e);
   if (const char* e = getenv("CAPITAL_DIST_CHUNKS")) D.chunks = atoi(e);
   if (const char* e = getenv("CAPITAL_DIST_BULK")) D.bulk_class = atoi(e) != 0;
+  if (const char* e = getenv("CAPITAL_DIST_PIPELINE")) D.pipeline = atoi(e) != 0;
   if (ctx->no_overlap) D.two_stream = false;
   return CAPITAL_OK;
 }
@@ -605,7 +608,7 @@ capital_status_t product_pushed(Dist& D, int q, int64_t m, int64_t n, int64_t k,
     prev_nc = 0;
     return CAPITAL_OK;
   };
-  const bool pipelined = D.xmode == 1 && D.nsets[q] >= 3;
+  const bool pipelined = D.pipeline && D.xmode == 1 && D.nsets[q] >= 3;
   for (int64_t c0 = 0; c0 < n; c0 += cw) {
     const int64_t nc = std::min(cw, n - c0);
     PendingProduct cur;
@@ -1162,8 +1165,7 @@ capital_status_t sweep(Qr& q, double* Rout) {
   capital_ctx* ctx = q.ctx;
   cudaStream_t st = q.st;
   const int64_t n = q.n, lr = q.lr;
-  CAP_CUDA(cudaMemsetAsync(q.G, 0, (size_t)q.ldn * n * 8, st));
-  CAP_TRY(gemm_tn_splitk(ctx, st, n, n, lr, 1.0, q.Q, q.ldq, q.Q, q.ldq, q.G, q.ldn, CAPITAL_GEMM_C_UPPER));  // dsyrk 'U','T' (:15)
+  CAP_TRY(gemm_tn_splitk(ctx, st, n, n, lr, 1.0, q.Q, q.ldq, q.Q, q.ldq, q.G, q.ldn, CAPITAL_GEMM_C_UPPER));  // dsyrk 'U','T' (:15), deterministic split-k
   if (ctx->grid.size > 1) CAP_TRY(peer_allreduce_sum(ctx, st, q.G, q.ldn * n, q.ar));                          // policy.h:82
   CAP_CUDA(cudaMemsetAsync(q.Ri, 0, (size_t)q.ldn * n * 8, st));
   CAP_CUDA(cudaMemsetAsync(q.RiT, 0, (size_t)q.ldn * n * 8, st));
@@ -1458,7 +1460,6 @@ capital_status_t dist_cacqr_residual(capital_ctx* ctx, const double* A_local, in
   CAP_TRY(gemm_tn(ctx, st, n, lr, n, 1.0, R, ldn, Qt, ldn, -1.0, Et, ldn, CAPITAL_GEMM_A_UPPER));
   CAP_TRY(sumsq_block(ctx, st, n, lr, Et, ldn, 0, 0, 0, 1, ctx->d_scalars));
   // orthogonality (validate.hpp:7-35): ||Q^T Q - I||_F / sqrt(n^2)
-  CAP_CUDA(cudaMemsetAsync(G, 0, (size_t)ldn * n * 8, st));
   CAP_TRY(gemm_tn_splitk(ctx, st, n, n, lr, 1.0, Q, ldq, Q, ldq, G, ldn, 0));
   if (g.size > 1) CAP_TRY(peer_allreduce_sum(ctx, st, G, ldn * n, ar));
   CAP_TRY(sub_identity_local(ctx, st, n, G, ldn));

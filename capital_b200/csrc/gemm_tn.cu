@@ -16,6 +16,7 @@
 // four q -- hit 8 distinct chunks).  Out-of-range rows/columns are zero-filled by TMA, so ragged M/N/K
 // need no predicates in the main loop.
 #include "common.cuh"
+#include <algorithm>
 
 namespace {
 
@@ -31,6 +32,11 @@ struct GemmParams {
   double alpha, beta;
   double* C;
   long long ldc;
+  double* Ct;       // optional second output: the TRANSPOSE of the result, Ct[row * ldct + col] (tall-skinny apply of CholeskyQR2)
+  long long ldct;
+  double* kpart;    // split-k: partial tiles of chunk z go to kpart + z * kstride (deterministic two-stage reduction) instead of atomics
+  long long kstride, ldk;
+  int no_c;         // skip the store to C (only Ct is wanted)
   GemmXDev x;  // depth exchange fused into the epilogue (XMODE != 0)
 };
 
@@ -220,9 +226,14 @@ __global__ void __launch_bounds__(((BM / WM) * (BN / WN) + 4) * 32, MINB)
         const int row = m0 + wm * WM + i * 8 + g;
         if (row >= p.M || (upper_only && row > col + p.noff)) continue;
         double v = alpha * acc[i][j][e];
-        if (XMODE == 0 && p.ksplit > 1) { atomicAdd(cc + row, v); continue; }
+        if (XMODE == 0 && p.ksplit > 1) {
+          if (p.kpart) p.kpart[(long long)blockIdx.z * p.kstride + (long long)col * p.ldk + row] = v;
+          else atomicAdd(cc + row, v);
+          continue;
+        }
         if (beta != 0.0) v += beta * cc[row];
-        cc[row] = v;
+        if (XMODE != 0 || !p.no_c) cc[row] = v;
+        if (XMODE == 0 && p.Ct) p.Ct[(long long)row * p.ldct + col] = v;
         if (XMODE != 0) {  // mode 1: the partner's receive buffer for my partial; mode 2: the partner's replica of C
           for (int oi = 0; oi < nother; oi++) p.x.Cpeer[oi][coff + row] = v;
         }
@@ -261,11 +272,16 @@ capital_status_t make_map(capital_ctx* ctx, CUtensorMap* map, const double* base
   return CAPITAL_OK;
 }
 
+struct GemmExtra {
+  double* Ct = nullptr; int64_t ldct = 0; int no_c = 0;
+  double* kpart = nullptr; int64_t kstride = 0, ldk = 0;
+};
 template <class Cfg>
 capital_status_t launch(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, GemmOperands ops, double beta, double* C,
-                        int64_t ldc, int flags, int ksplit, int koff, int noff, const GemmXDev* x) {
+                        int64_t ldc, int flags, int ksplit, int koff, int noff, const GemmXDev* x, const GemmExtra* ex = nullptr) {
   constexpr int BM = Cfg::BM, BN = Cfg::BN;
   GemmParams p{};
+  if (ex) { p.Ct = ex->Ct; p.ldct = ex->ldct; p.no_c = ex->no_c; p.kpart = ex->kpart; p.kstride = ex->kstride; p.ldk = ex->ldk; }
   p.M = (int)m; p.N = (int)n; p.K = (int)k; p.flags = flags; p.alpha = alpha; p.beta = beta; p.C = C; p.ldc = ldc; p.ksplit = ksplit; p.koff = koff; p.noff = noff;
   p.ncls = ops.ncls;
   // TMA fetches 16-byte granules: a window that starts on an odd row (8-byte aligned only) cannot be addressed by
@@ -368,23 +384,82 @@ capital_status_t gemm_tn_init(capital_ctx* ctx) {
 // which tile configuration a product of this output shape runs with
 static inline bool gemm_uses_big(const capital_ctx* ctx, int64_t m, int64_t n) { return ceil_div(m, 128) * ceil_div(n, 128) >= ctx->num_sms; }
 
-// Split-K variant for short-and-fat products (the tall-skinny Gram matrix, cacqr.hpp:15): C += alpha A^T B with the
-// k range cut into `ksplit` chunks, partial tiles accumulated with FP64 atomics.  C must hold the addend on entry.
+// second stage of the deterministic split-k: C = sum over the chunks, in chunk order
+__global__ void splitk_reduce_kernel(long long rows, long long cols, const double* part, long long kstride, long long ldk, int nchunk, double* C,
+                                     long long ldc, int upper_only) {
+  const long long total = rows * cols;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long c = idx / rows, r = idx - c * rows;
+    if (upper_only && r > c) continue;
+    double s = 0.0;
+    for (int z = 0; z < nchunk; z++) s += part[(long long)z * kstride + c * ldk + r];
+    C[c * ldc + r] = s;
+  }
+}
+
+// Split-K variant for short-and-fat products (the tall-skinny Gram matrix, cacqr.hpp:15): C = alpha A^T B with the k range cut
+// into chunks, one CTA per (tile, chunk); the partial tiles go to a workspace and are added up in chunk order by a second kernel
+// (deterministic: the same bits on every run and on every rank).  128 x 128 tiles when the output has them: 3 upper tiles x 49
+// chunks fill the 148 SMs for a 256 x 256 Gram matrix.
 capital_status_t gemm_tn_splitk(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
                                 int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int flags) {
   if (m <= 0 || n <= 0 || k <= 0) return CAPITAL_OK;
   if (lda < k || ldb < k || ldc < m || (lda & 1) || (ldb & 1)) return CAPITAL_ERR_INVALID;
-  const int64_t tiles = ceil_div(m, 64) * ceil_div(n, 64);
-  int64_t ks = ceil_div((int64_t)ctx->num_sms * 2, tiles);
+  const bool big = m >= 128 && n >= 128;
+  const int64_t t = big ? 128 : 64;
+  const int64_t gm = ceil_div(m, t), gn = ceil_div(n, t);
+  int64_t tiles = gm * gn;
+  if ((flags & CAPITAL_GEMM_C_UPPER) && gm == gn) tiles = gm * (gm + 1) / 2;  // tiles below the diagonal return at once
+  int64_t ks = ceil_div((int64_t)ctx->num_sms * (big ? 1 : 2), tiles);
   const int64_t max_ks = ceil_div(k, 16 * 32);  // at least 32 k-tiles per chunk
   if (ks > max_ks) ks = max_ks;
   if (ks < 1) ks = 1;
-  ctx->counters.kernel_launches++;
+  ctx->counters.kernel_launches += 2;
   ctx->counters.gemm_launches++;
   ctx->counters.gemm_flops += 2.0 * (double)m * (double)n * (double)k * ((flags & CAPITAL_GEMM_C_UPPER) ? 0.5 : 1.0);
   GemmOperands ops;
   ops.A[0] = A; ops.B[0] = B; ops.lda = lda; ops.ldb = ldb;
-  return launch<CfgSmall>(ctx, st, m, n, k, alpha, ops, 1.0, C, ldc, flags, (int)ks, 0, 0, nullptr);
+  if (ks == 1) {  // one chunk: the tile is stored straight into C
+    ctx->counters.kernel_launches--;
+    if (big) return launch<CfgBig>(ctx, st, m, n, k, alpha, ops, 0.0, C, ldc, flags, 1, 0, 0, nullptr);
+    return launch<CfgSmall>(ctx, st, m, n, k, alpha, ops, 0.0, C, ldc, flags, 1, 0, 0, nullptr);
+  }
+  GemmExtra ex;
+  ex.ldk = round_up(m, 2); ex.kstride = ex.ldk * n;
+  CAP_TRY(ctx->workspace("splitk_part", (size_t)ks * ex.kstride * 8, (void**)&ex.kpart));
+  const int tli = ctx->tl_begin(st, big ? 1 : 2, (double)m, (double)n, (double)k);
+  if (big) CAP_TRY((launch<CfgBig>(ctx, st, m, n, k, alpha, ops, 0.0, C, ldc, flags, (int)ks, 0, 0, nullptr, &ex)));
+  else CAP_TRY((launch<CfgSmall>(ctx, st, m, n, k, alpha, ops, 0.0, C, ldc, flags, (int)ks, 0, 0, nullptr, &ex)));
+  ctx->tl_end(st, tli);
+  const long long total = m * n;
+  const int gr = (int)std::min<long long>((total + 255) / 256, (long long)ctx->num_sms * 4);
+  splitk_reduce_kernel<<<gr, 256, 0, st>>>(m, n, ex.kpart, ex.kstride, ex.ldk, (int)ks, C, ldc, (flags & CAPITAL_GEMM_C_UPPER) ? 1 : 0);
+  CAP_CUDA(cudaGetLastError());
+  return CAPITAL_OK;
+}
+
+// C = alpha A^T B with the result ALSO (or only, C == nullptr) stored transposed into Ct (ldct).  The tall-skinny apply of
+// CholeskyQR2, Q <- Q Rinv, is computed as (Q Rinv)^T = Rinv^T Q^T with K-contiguous operands; the transposed store writes Q back in
+// its column-major layout from the epilogue (no separate transpose pass), the plain store keeps Q^T for the next sweep.
+capital_status_t gemm_tn_t(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
+                           const double* B, int64_t ldb, double* C, int64_t ldc, double* Ct, int64_t ldct, int flags) {
+  if (m <= 0 || n <= 0 || k <= 0) return CAPITAL_OK;
+  if (lda < k || ldb < k || (C && ldc < m) || !Ct || ldct < n || (lda & 1) || (ldb & 1)) return CAPITAL_ERR_INVALID;
+  ctx->counters.kernel_launches++;
+  ctx->counters.gemm_launches++;
+  const bool atri = flags & (CAPITAL_GEMM_A_UPPER | CAPITAL_GEMM_A_LOWER);
+  ctx->counters.gemm_flops += atri ? (double)n * (double)m * (double)(m + 1) : 2.0 * (double)m * (double)n * (double)k;
+  GemmOperands ops;
+  ops.A[0] = A; ops.B[0] = B; ops.lda = lda; ops.ldb = ldb;
+  GemmExtra ex;
+  ex.Ct = Ct; ex.ldct = ldct; ex.no_c = C ? 0 : 1;
+  const bool big = gemm_uses_big(ctx, m, n);
+  const int tli = ctx->tl_begin(st, big ? 1 : 2, (double)m, (double)n, (double)k);
+  capital_status_t rs;
+  if (big) rs = launch<CfgBig>(ctx, st, m, n, k, alpha, ops, 0.0, C ? C : Ct, C ? ldc : m, flags, 1, 0, 0, nullptr, &ex);
+  else rs = launch<CfgSmall>(ctx, st, m, n, k, alpha, ops, 0.0, C ? C : Ct, C ? ldc : m, flags, 1, 0, 0, nullptr, &ex);
+  ctx->tl_end(st, tli);
+  return rs;
 }
 
 // Same product issued as a sequence of k-chunked launches (C accumulates).  Used for deferred work on the low-priority

@@ -195,6 +195,25 @@ def test_flag_protocol_is_deadlock_free_and_race_free(size, n, ci, bcm, monkeypa
     assert not bad, f"{len(bad)} unordered conflicting accesses, e.g. {bad[:3]}"
 
 
+def test_pipelined_chunked_products_are_clean_too(monkeypatch):
+    """opt-in CAPITAL_DIST_PIPELINE=1: chunk j + 1 is issued before chunk j is added up (three rotating exchange sets + the
+    'reduced' flag keep a partner from overwriting a set that is still being read)"""
+    monkeypatch.setenv("CAPITAL_DIST_PIPELINE", "1")
+    monkeypatch.setenv("CAPITAL_DIST_CHUNK_MIN", "256")
+    monkeypatch.setenv("CAPITAL_DIST_FAR_MIN", "64")
+    monkeypatch.setenv("CAPITAL_DIST_SIDE_MIN", "32")
+    traces = [trace(8, r, 2, 2048, 1, -3) for r in range(8)]
+    rp = Replay(traces)
+    assert not rp.run((2, 2))
+    assert not rp.races()
+    # and the flag that protects the rotating sets is load-bearing: without its waits the replay finds the race
+    CTRL_RED_LO, CTRL_RED_HI = 192, 272
+    mut = [tr[~((tr[:, 0] == T_WAIT) & (tr[:, 2] >= CTRL_RED_LO) & (tr[:, 2] < CTRL_RED_HI))] for tr in traces]
+    rp2 = Replay(mut)
+    assert not rp2.run((2, 2))
+    assert rp2.races()
+
+
 def test_single_stream_schedule_also_clean(monkeypatch):
     monkeypatch.setenv("CAPITAL_DIST_TWO_STREAM", "0")
     traces = [trace(8, r, 2, 1024, 1, -2) for r in range(8)]
