@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcapital_b200.so")
+LIB_PATH = os.environ.get("CAPITAL_B200_LIB") or os.path.join(_HERE, "libcapital_b200.so")  # (the env override lets tools/ bisect builds)
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NOT_SPD, ERR_COMM, ERR_UNSUPPORTED = range(6)
 RECT, UPPERTRI_PACKED = 0, 1

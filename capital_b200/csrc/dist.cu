@@ -1177,6 +1177,24 @@ capital_status_t sweep(Qr& q, double* Rout) {
   CAP_TRY(transpose_block(ctx, st, n, lr, q.Qt2, q.ldt, q.Q, q.ldq, 1.0));
   return CAPITAL_OK;
 }
+// The same sweep with every layout change folded into GEMM epilogues [default; CAPITAL_QR_TSTORE=0 selects the plain sweep above]:
+//   Qc   : the panel, column-major (lr x n), read by the Gram product (K = rows, contiguous)
+//   QtIn : its transpose (n x lr), read by the apply
+//   QtOut: (optional) transpose of the updated panel = plain store of the apply, for the next sweep
+//   QcOut: the updated panel, column-major = TRANSPOSED store of the apply's epilogue (no separate transpose pass)
+capital_status_t sweep_tstore(Qr& q, const double* Qc, int64_t ldqc, const double* QtIn, double* QtOut, double* QcOut, int64_t ldqo, double* Rout) {
+  capital_ctx* ctx = q.ctx;
+  cudaStream_t st = q.st;
+  const int64_t n = q.n, lr = q.lr;
+  CAP_TRY(gemm_tn_splitk(ctx, st, n, n, lr, 1.0, Qc, ldqc, Qc, ldqc, q.G, q.ldn, CAPITAL_GEMM_C_UPPER));  // dsyrk 'U','T' (:15)
+  if (ctx->grid.size > 1) CAP_TRY(peer_allreduce_sum(ctx, st, q.G, q.ldn * n, q.ar));                    // policy.h:82
+  CAP_CUDA(cudaMemsetAsync(q.Ri, 0, (size_t)q.ldn * n * 8, st));
+  CAP_CUDA(cudaMemsetAsync(q.RiT, 0, (size_t)q.ldn * n * 8, st));
+  CAP_CUDA(cudaMemsetAsync(Rout, 0, (size_t)q.ldn * n * 8, st));
+  CAP_TRY(cholinv_local(ctx, st, n, q.G, q.ldn, Rout, q.ldn, q.Ri, q.ldn, q.RiT, q.ldn, true, n, 1));  // potrf + trtri (:20-22)
+  // Q <- Q Rinv (dtrmm Right/Upper/NoTrans, :25): (Q Rinv)^T = Rinv^T Q^T, A = Rinv (upper), B = Q^T
+  return gemm_tn_t(ctx, st, n, lr, n, 1.0, q.Ri, q.ldn, QtIn, q.ldt, QtOut, q.ldt, QcOut, ldqo, CAPITAL_GEMM_A_UPPER);
+}
 // small all-reduce scratch of the 1D path: an arena region of 2 * size * count doubles
 capital_status_t qr1d_arena(capital_ctx* ctx, int64_t count, double** ar) {
   *ar = nullptr;
@@ -1408,11 +1426,35 @@ capital_status_t dist_cacqr_factor(capital_ctx* ctx, const double* A_local, int6
   CAP_TRY(ctx->workspace("qrRt", nn, (void**)&q.Rt));
   CAP_TRY(qr1d_arena(ctx, q.ldn * n, &q.ar));
   CAP_CUDA(cudaMemsetAsync(ctx->d_info, 0, sizeof(int), st));
-  CAP_TRY(copy_block(ctx, st, lr, n, dA, lr, q.Q, q.ldq));  // Q <- A (cacqr.hpp:226)
-  CAP_TRY(sweep(q, q.R1));
+  const char* ets = getenv("CAPITAL_QR_TSTORE");
+  const bool tstore = !(ets && atoi(ets) == 0);
   const double* Rfinal = q.R1;
+  bool q_in_place = false;  // the final panel already sits in the caller's Q
+  if (tstore) {
+    // Q <- A (cacqr.hpp:226): the Gram product reads A where it lies when its leading dimension suits TMA (even, 16-byte aligned
+    // base); the apply wants the transpose, made once here -- every later layout change happens inside a GEMM epilogue
+    const double* Qc = dA;
+    int64_t ldqc = lr;
+    if ((lr & 1) || ((uintptr_t)dA & 15)) {
+      CAP_TRY(copy_block(ctx, st, lr, n, dA, lr, q.Q, q.ldq));
+      Qc = q.Q; ldqc = q.ldq;
+    }
+    CAP_TRY(transpose_block(ctx, st, lr, n, dA, lr, q.Qt, q.ldt, 1.0));
+    q_in_place = (dQ == Q_local);  // device output: the last apply writes it directly (leading dimension lr)
+    double* Qlast = q_in_place ? dQ : q.Q;
+    const int64_t ldlast = q_in_place ? lr : q.ldq;
+    if (num_iter > 1) {
+      CAP_TRY(sweep_tstore(q, Qc, ldqc, q.Qt, q.Qt2, q.Q, q.ldq, q.R1));
+      CAP_TRY(sweep_tstore(q, q.Q, q.ldq, q.Qt2, nullptr, Qlast, ldlast, q.R2));  // (the apply reads Q^T: the panel may be overwritten)
+    } else {
+      CAP_TRY(sweep_tstore(q, Qc, ldqc, q.Qt, nullptr, Qlast, ldlast, q.R1));
+    }
+  } else {
+    CAP_TRY(copy_block(ctx, st, lr, n, dA, lr, q.Q, q.ldq));  // Q <- A (cacqr.hpp:226)
+    CAP_TRY(sweep(q, q.R1));
+    if (num_iter > 1) CAP_TRY(sweep(q, q.R2));
+  }
   if (num_iter > 1) {
-    CAP_TRY(sweep(q, q.R2));
     // R = R2 R1 (dtrmm, cacqr.hpp:185-187) = (R2^T)^T R1 : A = R2^T (lower), B = R1 (upper)
     CAP_TRY(transpose_block(ctx, st, n, n, q.R2, q.ldn, q.Rt, q.ldn, 1.0));
     CAP_TRY(gemm_tn(ctx, st, n, n, n, 1.0, q.Rt, q.ldn, q.R1, q.ldn, 0.0, q.G, q.ldn,
@@ -1421,7 +1463,7 @@ capital_status_t dist_cacqr_factor(capital_ctx* ctx, const double* A_local, int6
   }
   if (rstruct == CAPITAL_UPPERTRI_PACKED) CAP_TRY(pack_upper(ctx, st, n, Rfinal, q.ldn, dR, 0));
   else CAP_TRY(triu_copy(ctx, st, n, Rfinal, q.ldn, dR, n, 0));
-  CAP_TRY(copy_block(ctx, st, lr, n, q.Q, q.ldq, dQ, lr));
+  if (!q_in_place) CAP_TRY(copy_block(ctx, st, lr, n, q.Q, q.ldq, dQ, lr));
   CAP_TRY(cap_stage_out_end(ctx, Q_local, (size_t)lr * n, dQ));
   CAP_TRY(cap_stage_out_end(ctx, R_local, r_count, dR));
   CAP_CUDA(cudaEventRecord(ctx->ev_stop, st));
