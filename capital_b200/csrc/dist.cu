@@ -102,6 +102,20 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(long long rows, lo
   }
 }
 
+// One system-scope load from every partner buffer the preceding GEMM stored into, issued between that GEMM and the flag that
+// announces it.  A read over NVLink cannot pass the posted writes of the same source to the same destination, so when it returns
+// the epilogue's remote stores have been delivered -- the flag itself travels from the stream's front end, not from the SMs, and
+// must not get there first.  (Belt and braces on top of the membar.sys every storing thread executes.)
+struct PeerTouch { const double* p[GEMM_XPEERS_MAX]; int n; };
+__global__ void flush_posted_writes_kernel(PeerTouch t, double* sink) {
+  if (threadIdx.x < t.n) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(t.p[threadIdx.x]) : "memory");
+    if (v == 1.2345678e300) sink[0] = v;  // keep the load alive
+  }
+  __threadfence_system();
+}
+
 inline int grid_for(const capital_ctx* ctx, long long total) {
   long long b = (total + 255) / 256;
   const long long cap = (long long)ctx->num_sms * 8;
@@ -179,6 +193,7 @@ struct Dist {
   int64_t chunk_min = 4096;  // R12 / Rinv12 blocks at least this wide are produced and pushed in `chunks` column chunks [env CAPITAL_DIST_CHUNK_MIN]
   int chunks = 4;            // [env CAPITAL_DIST_CHUNKS]
   bool bulk_class = true;    // node-entry pushes of A12 travel on their own push stream [env CAPITAL_DIST_BULK]
+  bool flush_reads = true;   // read back from the partners between a storing GEMM and its flag [env CAPITAL_DIST_FLUSH_READS]
   bool pipeline = false;     // chunked products issue chunk j + 1 before adding up chunk j (hides the layers' skew) [env CAPITAL_DIST_PIPELINE];
                              // protocol-checked, but off until it has a clean multi-GPU soak (profiles/r02c_coherence_bug_notes.md)
   // host-pointer callers: A arrives by column chunks on the copy-in stream; finished column ranges are packed and copied out while
@@ -354,6 +369,7 @@ capital_status_t dist_setup(Dist& D, capital_ctx* ctx, bool dry) {
   if (const char* e = getenv("CAPITAL_DIST_CHUNKS")) D.chunks = atoi(e);
   if (const char* e = getenv("CAPITAL_DIST_BULK")) D.bulk_class = atoi(e) != 0;
   if (const char* e = getenv("CAPITAL_DIST_PIPELINE")) D.pipeline = atoi(e) != 0;
+  if (const char* e = getenv("CAPITAL_DIST_FLUSH_READS")) D.flush_reads = atoi(e) != 0;
   if (ctx->no_overlap) D.two_stream = false;
   return CAPITAL_OK;
 }
@@ -473,6 +489,16 @@ inline std::vector<Flag> partner_flags(const Dist& D, size_t base, int q, unsign
   }
   return f;
 }
+capital_status_t flush_posted_writes(Dist& D, int sid, const GemmXDev& x) {
+  capital_ctx* ctx = D.ctx;
+  if (D.dry || !D.flush_reads) return CAPITAL_OK;
+  PeerTouch t{};
+  for (int i = 0; i < x.c - 1 && i < GEMM_XPEERS_MAX; i++) t.p[t.n++] = x.Cpeer[i];
+  flush_posted_writes_kernel<<<1, 32, 0, D.strm(sid)>>>(t, ctx->d_scalars + 15);
+  ctx->counters.kernel_launches++;
+  CAP_CUDA(cudaGetLastError());
+  return CAPITAL_OK;
+}
 capital_status_t product_issue(Dist& D, int q, int64_t m, int64_t n, int64_t k, double alpha, Win X, Win Y, double beta, Win C, int flags,
                                const Token* farX, const Token* farY, int noff, PendingProduct* pd) {
   capital_ctx* ctx = D.ctx;
@@ -525,7 +551,10 @@ capital_status_t product_issue(Dist& D, int q, int64_t m, int64_t n, int64_t k, 
       for (int l = 0; l < D.c; l++)
         if (l != D.g.z) D.wr(sid, rank_of(D.g, D.g.x, D.g.y, l), Cown, ldc, m, n, group);
       D.rec(T_PRODUCT, sid, q, (int64_t)seq, 2);
-    } else CAP_TRY(gemm_tn_x(ctx, D.strm(sid), m, n, k, alpha, ops, beta, Cown, ldc, flags, 0, noff, &x));
+    } else {
+      CAP_TRY(gemm_tn_x(ctx, D.strm(sid), m, n, k, alpha, ops, beta, Cown, ldc, flags, 0, noff, &x));
+      CAP_TRY(flush_posted_writes(D, sid, x));
+    }
     CAP_TRY(D.signal_flags(sid, partner_flags(D, CTRL_DONE, q, 2 * seq, true)));
     return D.wait_flags(sid, partner_flags(D, CTRL_DONE, q, 2 * seq, false));
   }
@@ -558,7 +587,10 @@ capital_status_t product_issue(Dist& D, int q, int64_t m, int64_t n, int64_t k, 
     for (int l = 0; l < D.c; l++)
       if (l != D.g.z) D.wr(sid, rank_of(D.g, D.g.x, D.g.y, l), recv_set + (size_t)(D.g.z < l ? D.g.z : D.g.z - 1) * stride, ldp, m, n);
     D.rec(T_PRODUCT, sid, q, (int64_t)seq, 1);
-  } else CAP_TRY(gemm_tn_x(ctx, D.strm(sid), m, n, k, alpha, ops, 0.0, own_set, ldp, flags, 0, noff, &x));
+  } else {
+    CAP_TRY(gemm_tn_x(ctx, D.strm(sid), m, n, k, alpha, ops, 0.0, own_set, ldp, flags, 0, noff, &x));
+    CAP_TRY(flush_posted_writes(D, sid, x));
+  }
   CAP_TRY(D.signal_flags(sid, partner_flags(D, CTRL_DONE, q, 2 * seq, true)));
   pd->active = true; pd->q = q; pd->seq = seq; pd->m = m; pd->n = n; pd->ldp = ldp; pd->ldc = ldc; pd->beta = beta; pd->Cown = Cown;
   pd->upper = (flags & CAPITAL_GEMM_C_UPPER) ? 1 : 0; pd->noff = noff;
