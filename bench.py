@@ -412,6 +412,17 @@ def ours(args):
         except Exception as ex:  # noqa
             cacqr = {"error": repr(ex)[:300]}
 
+    # DRAM traffic of the dominant kernel: only from an `ncu --set full` capture of THIS kernel source (hash-checked), else null
+    traffic, traffic_src = None, "no ncu --set full capture of this build of gemm_tn.cu travels with the repo"
+    try:
+        import hashlib
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")))
+        sha = hashlib.sha256(open(os.path.join(ROOT, "capital_b200", "csrc", "gemm_tn.cu"), "rb").read()).hexdigest()[:16]
+        if tj.get("gemm_tn_cu_sha256_16") == sha and world == 1:
+            traffic = tj["traffic_bytes_per_launch_mean"]
+            traffic_src = "profiles/r02_gemm_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum, mean of 3 launches, same gemm_tn.cu hash): " + tj["source"]
+    except Exception:
+        pass
     if rank == 0:
         ach = s_flops / (s_ms * 1e-3) / 1e12 if s_ms > 0 else None
         ach_ov = k_flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else None
@@ -427,7 +438,7 @@ def ours(args):
             "residual": residual,
             "roofline": {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": (ach / peak_tf) if ach else None,
-                         "traffic": None,  # no `ncu --set full` capture of THIS build travels with the run; see profiles/ for the last one
+                         "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": "gemm_tn_kernel<128,128,64,32,5> (DMMA.8x8x4 + TMA" + (", depth exchange fused in the epilogue)" if world > 1 else ")"),
                          "launches": s_launches,
                          "kernel_share_of_step": s_ms / s_ms_step if s_ms_step else None,
