@@ -1,5 +1,6 @@
 """Consistency probe of the distributed cholinv::factor: residual, bit-identical replicas across the depth layers, run-to-run
-determinism.  torchrun --nproc-per-node N tools/dist_check.py n bcm c reps   (CAPITAL_MP_SAME_DEVICE=1: all ranks on cuda:0)"""
+determinism.  torchrun --nproc-per-node N tools/dist_check.py n bcm c reps   (CAPITAL_MP_SAME_DEVICE=1: the ranks share the visible
+GPUs round-robin -- 8 ranks on 1 GPU, or 4 + 4 on two GPUs with real NVLink traffic between the halves)"""
 import os, sys, hashlib
 import torch, torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -9,8 +10,8 @@ import capital_b200 as cb
 def main():
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     n, bcm, c, reps = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
-    same = bool(os.environ.get("CAPITAL_MP_SAME_DEVICE"))
-    torch.cuda.set_device(0 if same else lr)
+    same = bool(os.environ.get("CAPITAL_MP_SAME_DEVICE"))  # ranks share the visible GPUs round-robin (gloo bootstrap, CUDA IPC)
+    torch.cuda.set_device(lr % torch.cuda.device_count() if same else lr)
     dist.init_process_group("gloo" if same else "nccl", **({} if same else {"device_id": torch.device("cuda", lr)}))
     topo = cb.topo.square(world, rank, c)
     A = cb.matrix(n, n, topo.d, topo.d).distribute_symmetric(topo)
