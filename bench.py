@@ -448,6 +448,8 @@ def ours(args):
                          "peak_source": peak_src},
             "e2e": e2e, "gpu_launches": int(cnt.kernel_launches), "clocks": summarize_clocks(samples),
         }
+        if world > 1:
+            out["config"]["peer_flag_wait"] = ctx.peer_wait_mode()
         if timeline is not None:
             out["timeline"] = timeline
         if parity is not None:

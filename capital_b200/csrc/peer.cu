@@ -5,6 +5,7 @@
 #include "dist.cuh"
 #include <dlfcn.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -105,7 +106,7 @@ bool memops_load() {
   g_batch = (fn_batch)p;
   return true;
 }
-capital_status_t memops_issue(capital_ctx* ctx, cudaStream_t st, const FlagList& fl, bool wait) {
+capital_status_t memops_issue(capital_ctx* ctx, cudaStream_t st, const FlagList& fl, bool wait, bool flush = false) {
   CUstreamBatchMemOpParams ops[24];
   memset(ops, 0, sizeof(ops));
   for (int i = 0; i < fl.n; i++) {
@@ -113,7 +114,11 @@ capital_status_t memops_issue(capital_ctx* ctx, cudaStream_t st, const FlagList&
       ops[i].waitValue.operation = CU_STREAM_MEM_OP_WAIT_VALUE_64;
       ops[i].waitValue.address = (CUdeviceptr)fl.p[i];
       ops[i].waitValue.value64 = fl.v[i];
-      ops[i].waitValue.flags = CU_STREAM_WAIT_VALUE_GEQ;
+      // FLUSH: "the device is permitted to reorder remote writes internally" (cuda.h, CUstreamWaitValue_flags) -- without it a
+      // wait satisfied by a peer's flag does not make that peer's EARLIER stores (partial sums written by its GEMM epilogue over
+      // NVLink) visible to the kernels that follow the wait.  Observed as 1e-10-level, run-to-run varying errors at n = 32768 on
+      // real NVLink (profiles/r02c_coherence_bug_notes.md).
+      ops[i].waitValue.flags = CU_STREAM_WAIT_VALUE_GEQ | (flush ? CU_STREAM_WAIT_VALUE_FLUSH : 0);
     } else {
       ops[i].writeValue.operation = CU_STREAM_MEM_OP_WRITE_VALUE_64;
       ops[i].writeValue.address = (CUdeviceptr)fl.p[i];
@@ -161,6 +166,31 @@ capital_status_t peer_init(capital_ctx* ctx, peer_allgather_fn ag, void* user) {
   CAP_CUDA(cudaMemset(P->ctrl, 0, CTRL_WORDS * 8));
   if (const char* e = getenv("CAPITAL_PEER_MEMOPS")) P->memops = atoi(e) != 0;
   if (P->memops && !memops_load()) P->memops = false;
+  // How a stream waits for a flag a peer writes (see memops_issue): a memory-op wait must carry the remote-write flush; where
+  // the device cannot flush (or the driver refuses the flag) the wait is a one-warp kernel spinning on ld.acquire.sys instead.
+  P->wait_mode = PEER_WAIT_KERNEL;
+  if (P->memops) {
+    int dev = 0, can = 0;
+    CAP_CUDA(cudaGetDevice(&dev));
+    if (cudaDeviceGetAttribute(&can, cudaDevAttrCanFlushRemoteWrites, dev) != cudaSuccess) { can = 0; cudaGetLastError(); }
+    if (can) {
+      // refuse-proof: one already-satisfied flushed wait on this rank's own control block
+      FlagList t;
+      t.add(P->ctrl + CTRL_WORDS - 1, 0);
+      cudaStream_t ts;
+      CAP_CUDA(cudaStreamCreateWithFlags(&ts, cudaStreamNonBlocking));
+      const bool ok = memops_issue(ctx, ts, t, true, true) == CAPITAL_OK && cudaStreamSynchronize(ts) == cudaSuccess;
+      cudaStreamDestroy(ts);
+      if (ok) P->wait_mode = PEER_WAIT_MEMOP_FLUSH;
+      else { cudaGetLastError(); ctx->set_error(""); }
+    }
+  }
+  if (const char* e = getenv("CAPITAL_PEER_WAIT")) {
+    // "memop" = round-2 behaviour up to here (unflushed; kept to reproduce the bug), "flush", "kernel"
+    if (!strcmp(e, "kernel")) P->wait_mode = PEER_WAIT_KERNEL;
+    else if (P->memops && !strcmp(e, "flush")) P->wait_mode = PEER_WAIT_MEMOP_FLUSH;
+    else if (P->memops && !strcmp(e, "memop")) P->wait_mode = PEER_WAIT_MEMOP;
+  }
   cudaIpcMemHandle_t mine;
   CAP_CUDA(cudaIpcGetMemHandle(&mine, P->ctrl));
   std::vector<cudaIpcMemHandle_t> all(g.size);
@@ -247,8 +277,9 @@ capital_status_t peer_signal(capital_ctx* ctx, cudaStream_t st, const FlagList& 
 capital_status_t peer_wait(capital_ctx* ctx, cudaStream_t st, const FlagList& fl) {
   if (fl.n == 0) return CAPITAL_OK;
   const int tli = ctx->tl_begin(st, 5, fl.n);
-  if (peer_of(ctx)->memops) {
-    const capital_status_t rs = memops_issue(ctx, st, fl, true);
+  const int wm = peer_of(ctx)->wait_mode;
+  if (wm != PEER_WAIT_KERNEL) {
+    const capital_status_t rs = memops_issue(ctx, st, fl, true, wm == PEER_WAIT_MEMOP_FLUSH);
     ctx->tl_end(st, tli);
     return rs;
   }
@@ -325,6 +356,11 @@ extern "C" capital_status_t capital_comm_init(capital_ctx* ctx, const void* uid)
   const capital_status_t st = peer_init(ctx, nccl_allgather, ctx);
   if (st != CAPITAL_OK) peer_destroy(ctx);  // never leave a half-built clique behind
   return st;
+}
+
+extern "C" int capital_peer_wait_mode(const capital_ctx* ctx) {
+  if (!ctx || !ctx->peer) return -1;
+  return ((const Peer*)ctx->peer)->wait_mode;
 }
 
 extern "C" capital_status_t capital_comm_init_host(capital_ctx* ctx, capital_allgather_fn allgather, void* user) {

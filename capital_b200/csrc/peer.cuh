@@ -28,6 +28,7 @@ constexpr size_t CTRL_BAR = CTRL_DONE + PEER_MAX_RANKS * PEER_Q;  // [src]      
 constexpr size_t CTRL_AR = CTRL_BAR + PEER_MAX_RANKS;             // [src]      small all-reduce epochs
 constexpr size_t CTRL_RED = CTRL_AR + PEER_MAX_RANKS;             // [src][q]   "I have added up the partials of product v of class q"
 constexpr size_t CTRL_WORDS = 512;
+enum { PEER_WAIT_MEMOP = 0, PEER_WAIT_MEMOP_FLUSH = 1, PEER_WAIT_KERNEL = 2 };
 static_assert(CTRL_RED + PEER_MAX_RANKS * PEER_Q <= CTRL_WORDS, "control block too small");
 
 typedef int (*peer_allgather_fn)(void* user, const void* send, void* recv, int64_t bytes_per_rank);
@@ -52,6 +53,7 @@ struct Peer {
   unsigned long long push_id[PEER_Q] = {};          // logical push events issued so far (same on every rank)
   unsigned long long prod_seq[PEER_QC] = {};        // products with a depth exchange issued so far
   unsigned long long bar_epoch = 0, ar_epoch = 0;
+  int wait_mode = 2;    // PEER_WAIT_*: how a stream waits for a peer-written flag [env CAPITAL_PEER_WAIT]
   bool memops = true;   // flags through stream memory operations (no SM needed) instead of one-warp kernels [env CAPITAL_PEER_MEMOPS]
   // NCCL bootstrap (only when capital_comm_init was used)
   void* d_stage = nullptr;

@@ -87,6 +87,10 @@ capital_status_t capital_comm_init(capital_ctx* ctx, const void* nccl_unique_id)
  * matrix data never goes through it.  Must return 0 on success; recv holds size * bytes. */
 typedef int (*capital_allgather_fn)(void* user, const void* send, void* recv, int64_t bytes_per_rank);
 capital_status_t capital_comm_init_host(capital_ctx* ctx, capital_allgather_fn allgather, void* user);
+/* How this rank's streams wait for a flag written by a peer GPU: 0 = stream memory-op wait, 1 = memory-op wait followed by a flush
+ * of outstanding remote writes (CU_STREAM_WAIT_VALUE_FLUSH; the default where the device supports it), 2 = one-warp kernel spinning
+ * on ld.acquire.sys, -1 = the context has not joined a clique.  Override: env CAPITAL_PEER_WAIT = memop | flush | kernel. */
+int capital_peer_wait_mode(const capital_ctx* ctx);
 void capital_destroy(capital_ctx* ctx);
 const char* capital_last_error(const capital_ctx* ctx);
 capital_status_t capital_get_counters(const capital_ctx* ctx, capital_counters_t* out);

@@ -55,6 +55,11 @@ def test_cholinv_info_validates_like_the_reference_asserts():
         cb.cholinv.info(1, 1, 0, "L")
 
 
+def test_peer_wait_mode_without_a_clique():
+    # -1 = "this context has not joined a clique" (also for NULL): no compute, no GPU needed
+    assert _lib.lib().capital_peer_wait_mode(None) == -1
+
+
 def test_create_fails_loudly_without_device():
     import torch
     if torch.cuda.is_available():

@@ -31,7 +31,7 @@ def main():
             rep_ok = all(len(v) == 1 for v in byxy.values())
             print(f"n={n} bcm={bcm} rep {rep}: residual {max(a[4] for a in allh):.3e} replicas identical: {rep_ok} hashes {sorted(set(a[3] for a in allh))[:4]}", flush=True)
     if rank == 0:
-        print(f"  deterministic across reps (rank 0): {len(set(sums)) == 1}", flush=True)
+        print(f"  deterministic across reps (rank 0): {len(set(sums)) == 1}; peer flag waits: {topo.context().peer_wait_mode()}", flush=True)
     dist.barrier()
     cb.topo.release_contexts()
     dist.destroy_process_group()
