@@ -75,7 +75,9 @@ __global__ void wait_kernel(FlagList fl, int* err) {
       if (got >= fl.v[i]) break;
       __nanosleep(100);
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if (t1 - t0 > 20000000000ull) { atomicExch(err, -1); break; }  // a peer died or the schedules diverged: report, do not hang
+      // a peer died or the schedules diverged: report, do not hang.  Generous (ranks may legitimately be seconds apart, e.g. while
+      // one of them pins host memory); once a wait has given up, the ones queued behind it give up at once.
+      if (t1 - t0 > 120000000000ull || *(volatile int*)err == -1) { atomicExch(err, -1); break; }
     }
   }
   __syncthreads();
