@@ -412,6 +412,23 @@ def ours(args):
         except Exception as ex:  # noqa
             cacqr = {"error": repr(ex)[:300]}
 
+    # ---- EXPERIMENTAL (BASELINE config 5, off by default in the library): trailing updates on the TF32 tensor cores ----
+    # Child process: the tcgen05 kernel was written without GPU access and has its own CUDA context here, so that nothing it does can
+    # touch the numbers above.  Single GPU only in the bench; the c = 1 grids take the same path through dist.cu.
+    tf32 = None
+    if world == 1 and not args.no_extra and not args.n:
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "tf32_worker.py"), "bench", str(n), str(bcm), "3"],
+                               capture_output=True, text=True, timeout=240)
+            if r.returncode == 0:
+                tf32 = json.loads(r.stdout.strip().splitlines()[-1])
+                tf32["dtype"] = "tf32 (tcgen05.mma.kind::tf32, FP32 accumulation in TMEM) for A22 -= R12^T R12 with k >= 256; everything else f64"
+                tf32["status"] = "experimental: first executed by whoever runs this; see tests/test_gpu_zz_tf32.py for the parity gates"
+            else:
+                tf32 = {"error": r.stderr[-300:]}
+        except Exception as ex:  # noqa
+            tf32 = {"error": repr(ex)[:300]}
+
     # DRAM traffic of the dominant kernel: only from an `ncu --set full` capture of THIS kernel source (hash-checked), else null
     traffic, traffic_src = None, "no ncu --set full capture of this build of gemm_tn.cu travels with the repo"
     try:
@@ -456,6 +473,8 @@ def ours(args):
             out["parity"] = parity
         if strong is not None:
             out["strong"] = strong
+        if tf32 is not None:
+            out["mixed_precision_tf32"] = tf32
         if cacqr is not None:
             out["cacqr"] = cacqr
         if world == 1 and not args.no_cpu:

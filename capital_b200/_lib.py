@@ -14,7 +14,7 @@ GEMM_A_UPPER, GEMM_A_LOWER, GEMM_B_UPPER, GEMM_B_LOWER, GEMM_C_UPPER = 1, 2, 4, 
 EXPORTS = [  # every symbol include/capital_b200.h declares
     "capital_grid_square", "capital_grid_rect", "capital_cholinv_bc_dimension", "capital_create",
     "capital_comm_unique_id", "capital_comm_init", "capital_comm_init_host", "capital_peer_wait_mode", "capital_dist_trace_cholinv", "capital_destroy", "capital_last_error", "capital_get_counters",
-    "capital_reset_counters", "capital_synchronize", "capital_set_stream", "capital_release_workspace", "capital_last_factor_ms", "capital_profile_begin", "capital_profile_end", "capital_probe_dmma_f64", "capital_timeline_begin", "capital_timeline_end", "capital_set_overlap", "capital_distribute_symmetric_f64",
+    "capital_reset_counters", "capital_synchronize", "capital_set_stream", "capital_release_workspace", "capital_last_factor_ms", "capital_profile_begin", "capital_profile_end", "capital_probe_dmma_f64", "capital_blas_gemm_tn_tf32", "capital_set_trailing_precision", "capital_tf32_stats", "capital_timeline_begin", "capital_timeline_end", "capital_set_overlap", "capital_distribute_symmetric_f64",
     "capital_distribute_random_f64", "capital_cholinv_factor_f64", "capital_cholinv_residual_f64",
     "capital_cacqr_factor_f64", "capital_cacqr_residual_f64", "capital_summa_gemm_tn_f64", "capital_blas_gemm_tn_f64",
     "capital_lapack_potrf_trtri_f64",
@@ -62,6 +62,9 @@ def lib() -> C.CDLL:
     L.capital_comm_unique_id.argtypes = [vp]
     L.capital_comm_init.argtypes = [vp, vp]
     L.capital_comm_init_host.argtypes = [vp, ALLGATHER_FN, vp]
+    L.capital_blas_gemm_tn_tf32.argtypes = [vp, i64, i64, i64, dbl, vp, i64, vp, i64, dbl, vp, i64, ci, ci]
+    L.capital_set_trailing_precision.argtypes = [vp, ci]
+    L.capital_tf32_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(dbl)]
     L.capital_peer_wait_mode.argtypes = [vp]
     L.capital_peer_wait_mode.restype = C.c_int
     L.capital_dist_trace_cholinv.argtypes = [C.POINTER(Grid), i64, C.POINTER(CholinvArgs), C.POINTER(i64), i64, C.POINTER(i64)]
@@ -129,6 +132,15 @@ class Context:
 
     def set_stream(self, stream: int):
         self.check(lib().capital_set_stream(self._h, C.c_void_p(stream)))
+
+    def set_trailing_precision(self, mode: int):
+        """EXPERIMENTAL (BASELINE config 5): 0 = FP64 trailing updates (default), 1 = TF32 tensor cores, 3 = 3 x TF32 split operands."""
+        self.check(lib().capital_set_trailing_precision(self._h, mode))
+
+    def tf32_stats(self):
+        n, f = C.c_int64(), C.c_double()
+        self.check(lib().capital_tf32_stats(self._h, C.byref(n), C.byref(f)))
+        return int(n.value), float(f.value)
 
     def peer_wait_mode(self) -> str:
         """how this rank's streams wait for a peer-written flag (capital_peer_wait_mode)"""

@@ -85,6 +85,10 @@ capital_status_t cap_check_info(capital_ctx* ctx) {
   int info = 0;
   CAP_CUDA(cudaMemcpyAsync(&info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CAP_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (info == -3) {
+    ctx->set_error("the experimental TF32 trailing-update kernel gave up on an mbarrier wait (gemm_tf32.cu watchdog): results are invalid");
+    return CAPITAL_ERR_CUDA;
+  }
   if (info < 0) {
     ctx->set_error("a wait on a peer GPU timed out (a rank of the grid died, or the ranks did not make the same sequence of calls)");
     return CAPITAL_ERR_COMM;
@@ -346,7 +350,8 @@ capital_status_t capital_create(capital_ctx** out, const capital_grid_t* grid, i
   ok = ok && cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn != nullptr;
   if (!ok) { capital_destroy(ctx); return CAPITAL_ERR_CUDA; }
   ctx->encode = (cuTensorMapEncodeTiled_fn)fn;
-  if (gemm_tn_init(ctx) != CAPITAL_OK || leaf_init(ctx) != CAPITAL_OK) { capital_destroy(ctx); return CAPITAL_ERR_CUDA; }
+  if (gemm_tn_init(ctx) != CAPITAL_OK || leaf_init(ctx) != CAPITAL_OK || gemm_tf32_init(ctx) != CAPITAL_OK) { capital_destroy(ctx); return CAPITAL_ERR_CUDA; }
+  if (const char* e = getenv("CAPITAL_TF32_MIN_K")) ctx->tf32_min_k = atoll(e);
   if (const char* e = getenv("CAPITAL_KCHUNK")) ctx->kchunk = atoll(e);
   if (const char* e = getenv("CAPITAL_FAR_MIN")) ctx->far_min = atoll(e);
   if (const char* e = getenv("CAPITAL_SIDE_MIN")) ctx->side_min = atoll(e);
@@ -710,6 +715,30 @@ capital_status_t capital_blas_gemm_tn_f64(capital_ctx* ctx, int64_t m, int64_t n
     return CAPITAL_ERR_INVALID;
   }
   return gemm_tn(ctx, ctx->stream, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags);
+}
+// EXPERIMENTAL (BASELINE config 5): the same product on the TF32 tensor cores (tcgen05 + TMEM), FP64 in and out
+capital_status_t capital_blas_gemm_tn_tf32(capital_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
+                                           const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags, int passes) {
+  if (!ctx || !A || !B || !C) return CAPITAL_ERR_INVALID;
+  CAP_CUDA(cudaSetDevice(ctx->device));
+  if (!cap_is_device_ptr(A) || !cap_is_device_ptr(B) || !cap_is_device_ptr(C)) {
+    ctx->set_error("capital_blas_gemm_tn_tf32 takes device pointers");
+    return CAPITAL_ERR_INVALID;
+  }
+  CAP_CUDA(cudaMemsetAsync(ctx->d_info, 0, sizeof(int), ctx->stream));
+  CAP_TRY(gemm_tn_tf32(ctx, ctx->stream, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags, passes));
+  return cap_check_info(ctx);
+}
+capital_status_t capital_set_trailing_precision(capital_ctx* ctx, int mode) {
+  if (!ctx) return CAPITAL_ERR_INVALID;
+  if (mode != 0 && mode != 1 && mode != 3) { ctx->set_error("trailing precision: 0 (FP64), 1 (TF32) or 3 (3 x TF32, split operands)"); return CAPITAL_ERR_INVALID; }
+  ctx->trailing_mode = mode;
+  return CAPITAL_OK;
+}
+capital_status_t capital_tf32_stats(const capital_ctx* ctx, int64_t* launches, double* flops) {
+  if (!ctx || !launches || !flops) return CAPITAL_ERR_INVALID;
+  *launches = ctx->tf32_launches; *flops = ctx->tf32_flops;
+  return CAPITAL_OK;
 }
 capital_status_t capital_lapack_potrf_trtri_f64(capital_ctx* ctx, int64_t n, const double* A, int64_t lda, double* R, int64_t ldr,
                                                 double* Rinv, int64_t ldri) {

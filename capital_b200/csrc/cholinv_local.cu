@@ -129,13 +129,24 @@ capital_status_t rec(Rec& r, int64_t o, int64_t n, bool complete, cudaEvent_t pe
   // trailing update (cholinv.hpp:131-134): A22 -= R12^T R12, upper tiles only.
   // near = what the right child's left subtree reads (leading h x h block), far = everything else.
   const int64_t h = choose_split(r, o + s1, s2, true);
+  // experimental mixed precision (BASELINE config 5): this product, and only this one, may run on the TF32 tensor cores
+  const int tf = trailing_uses_tf32(ctx, s1) ? ctx->trailing_mode : 0;
   if (use_side && h > 0 && s2 >= r.far_min) {
-    CAP_TRY(gemm_tn(ctx, r.M, h, h, s1, -1.0, R12, ldr, R12, ldr, 1.0, W22, ldw, CAPITAL_GEMM_C_UPPER));
-    CAP_TRY(gemm_tn_chunked(ctx, r.S, h, s2 - h, s1, -1.0, R12, ldr, R12 + h * ldr, ldr, 1.0, W22 + h * ldw, ldw, 0, r.kchunk));
-    CAP_TRY(gemm_tn_chunked(ctx, r.S, s2 - h, s2 - h, s1, -1.0, R12 + h * ldr, ldr, R12 + h * ldr, ldr, 1.0, W22 + h * ldw + h, ldw,
-                            CAPITAL_GEMM_C_UPPER, r.kchunk));
+    if (tf) {
+      CAP_TRY(gemm_tn_tf32(ctx, r.M, h, h, s1, -1.0, R12, ldr, R12, ldr, 1.0, W22, ldw, CAPITAL_GEMM_C_UPPER, tf));
+      CAP_TRY(gemm_tn_tf32(ctx, r.S, h, s2 - h, s1, -1.0, R12, ldr, R12 + h * ldr, ldr, 1.0, W22 + h * ldw, ldw, 0, tf));
+      CAP_TRY(gemm_tn_tf32(ctx, r.S, s2 - h, s2 - h, s1, -1.0, R12 + h * ldr, ldr, R12 + h * ldr, ldr, 1.0, W22 + h * ldw + h, ldw,
+                           CAPITAL_GEMM_C_UPPER, tf));
+    } else {
+      CAP_TRY(gemm_tn(ctx, r.M, h, h, s1, -1.0, R12, ldr, R12, ldr, 1.0, W22, ldw, CAPITAL_GEMM_C_UPPER));
+      CAP_TRY(gemm_tn_chunked(ctx, r.S, h, s2 - h, s1, -1.0, R12, ldr, R12 + h * ldr, ldr, 1.0, W22 + h * ldw, ldw, 0, r.kchunk));
+      CAP_TRY(gemm_tn_chunked(ctx, r.S, s2 - h, s2 - h, s1, -1.0, R12 + h * ldr, ldr, R12 + h * ldr, ldr, 1.0, W22 + h * ldw + h, ldw,
+                              CAPITAL_GEMM_C_UPPER, r.kchunk));
+    }
     CAP_TRY(new_event(ctx, &e_far));
     CAP_CUDA(cudaEventRecord(e_far, r.S));
+  } else if (tf) {
+    CAP_TRY(gemm_tn_tf32(ctx, r.M, s2, s2, s1, -1.0, R12, ldr, R12, ldr, 1.0, W22, ldw, CAPITAL_GEMM_C_UPPER, tf));
   } else {
     CAP_TRY(gemm_tn(ctx, r.M, s2, s2, s1, -1.0, R12, ldr, R12, ldr, 1.0, W22, ldw, CAPITAL_GEMM_C_UPPER));
   }

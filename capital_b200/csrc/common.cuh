@@ -80,6 +80,12 @@ struct capital_ctx {
   int64_t far_min = 2048;   // trailing updates at least this large are split into near (critical) / far (deferred)   [env CAPITAL_FAR_MIN]
   int64_t side_min = 1024;  // nodes whose left part is at least this large defer T^T to the low-priority stream      [env CAPITAL_SIDE_MIN]; swept in r01: 256 -> 68.9 ms, 1024 -> 67.0 ms
   bool no_overlap = false;  // debug / measurement: run the recursion on one stream
+  // EXPERIMENTAL, off by default (capital_set_trailing_precision): trailing updates A22 -= R12^T R12 on the TF32 tensor cores
+  // (gemm_tf32.cu); 0 = FP64 DMMA, 1 = TF32, 3 = 3 x TF32 with split operands.  Products with k below tf32_min_k stay FP64.
+  int trailing_mode = 0;
+  int64_t tf32_min_k = 256;
+  int64_t tf32_launches = 0;
+  double tf32_flops = 0.0;
   std::vector<cudaEvent_t> prof_pool;
   size_t prof_used = 0;
   std::vector<ProfRec> prof_recs;
@@ -148,6 +154,15 @@ capital_status_t gemm_tn_splitk(capital_ctx* ctx, cudaStream_t st, int64_t m, in
                                 int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int flags);
 capital_status_t gemm_tn_t(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
                            const double* B, int64_t ldb, double* C, int64_t ldc, double* Ct, int64_t ldct, int flags);
+
+// ---- gemm_tf32.cu (experimental mixed-precision trailing update, BASELINE config 5) ----------------------------
+capital_status_t gemm_tf32_init(capital_ctx* ctx);
+capital_status_t gemm_tn_tf32(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
+                              const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags, int passes);
+capital_status_t gemm_tn_tf32_x(capital_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const GemmOperands& ops,
+                                double beta, double* C, int64_t ldc, int flags, int noff, int passes);
+// the trailing update of one node: FP64 DMMA by default, TF32 when the context asks for it and the contraction is long enough
+static inline bool trailing_uses_tf32(const capital_ctx* ctx, int64_t k) { return ctx->trailing_mode != 0 && k >= ctx->tf32_min_k; }
 
 // ---- layout.cu --------------------------------------------------------------------------------
 capital_status_t transpose_block(capital_ctx* ctx, cudaStream_t st, int64_t rows, int64_t cols, const double* src,

@@ -125,6 +125,9 @@ inline int64_t packed_ld(int64_t rows) { return round_up(rows, 2); }
 
 // ---- the distributed machinery --------------------------------------------------------------------------------
 enum { ROLE_X = 1, ROLE_Y = 2, ROLE_T = 4, ROLE_G = 8 };
+// internal product flag (never reaches a kernel): this product is a trailing update A22 -= R12^T R12 -- the one product the
+// experimental mixed-precision mode may run on the TF32 tensor cores (gemm_tf32.cu; grids without a depth exchange only)
+constexpr int GEMM_TRAILING = 1 << 16;
 enum { Q_CHAIN = 0, Q_FAR0 = 1, Q_BULK = PEER_QC };  // deferred classes Q_FAR0 + depth, depth < PEER_NFAR
 enum { S_USER = 0, S_CHAIN = 1, S_FAR0 = 2, S_PUSH0 = S_FAR0 + PEER_NFAR, S_COPYIN = S_PUSH0 + PEER_Q, S_COPYOUT = S_COPYIN + 1, S_COUNT = S_COPYOUT + 1 };
 constexpr int NK_MAX = GEMM_NCLS_MAX;
@@ -504,6 +507,8 @@ capital_status_t product_issue(Dist& D, int q, int64_t m, int64_t n, int64_t k, 
   capital_ctx* ctx = D.ctx;
   Peer* P = D.P;
   const int sid = D.cstream(q);
+  const bool trailing = flags & GEMM_TRAILING;
+  flags &= ~GEMM_TRAILING;
   pd->active = false;
   if (m <= 0 || n <= 0 || k <= 0) return CAPITAL_OK;
   GemmOperands ops;
@@ -527,6 +532,8 @@ capital_status_t product_issue(Dist& D, int q, int64_t m, int64_t n, int64_t k, 
       for (int j = 0; j < D.nk; j++) { D.rd(sid, ops.A[j], ops.lda, k, m); D.rd(sid, ops.B[j], ops.ldb, k, n); }
       D.wr(sid, D.me, Cown, ldc, m, n);
       D.rec(T_PRODUCT, sid, q, 0, 0);
+    } else if (trailing && trailing_uses_tf32(ctx, k * D.nk)) {
+      CAP_TRY(gemm_tn_tf32_x(ctx, D.strm(sid), m, n, k, alpha, ops, beta, Cown, ldc, flags, noff, ctx->trailing_mode));
     } else CAP_TRY(gemm_tn_x(ctx, D.strm(sid), m, n, k, alpha, ops, beta, Cown, ldc, flags, 0, noff, nullptr));
     return CAPITAL_OK;
   }
@@ -804,14 +811,14 @@ capital_status_t invoke(Dist& D, int64_t o, int64_t s, bool complete, int pendin
   }
   if (use_side && h > 0 && s2 >= D.far_min) {
     const Win R12b{&D.R, o, o + s1 + h};
-    CAP_TRY(product(D, Q_CHAIN, h, h, s1, -1.0, R12, R12, 1.0, W22, CAPITAL_GEMM_C_UPPER));
-    CAP_TRY(product(D, fq, h, s2 - h, s1, -1.0, R12, R12b, 1.0, Win{&D.W, o + s1, o + s1 + h}, 0));
+    CAP_TRY(product(D, Q_CHAIN, h, h, s1, -1.0, R12, R12, 1.0, W22, CAPITAL_GEMM_C_UPPER | GEMM_TRAILING));
+    CAP_TRY(product(D, fq, h, s2 - h, s1, -1.0, R12, R12b, 1.0, Win{&D.W, o + s1, o + s1 + h}, GEMM_TRAILING));
     // that block is the right child's A12: its Y consumers get it as soon as it is final
     CAP_TRY(push(D, fq, fs, D.W, o + s1, o + s1 + h, h, s2 - h, ROLE_Y, &tChildW12));
-    CAP_TRY(product(D, fq, s2 - h, s2 - h, s1, -1.0, R12b, R12b, 1.0, Win{&D.W, o + s1 + h, o + s1 + h}, CAPITAL_GEMM_C_UPPER));
+    CAP_TRY(product(D, fq, s2 - h, s2 - h, s1, -1.0, R12b, R12b, 1.0, Win{&D.W, o + s1 + h, o + s1 + h}, CAPITAL_GEMM_C_UPPER | GEMM_TRAILING));
     CAP_TRY(D.ev_record(fs, &e_far));
   } else {
-    CAP_TRY(product(D, Q_CHAIN, s2, s2, s1, -1.0, R12, R12, 1.0, W22, CAPITAL_GEMM_C_UPPER));
+    CAP_TRY(product(D, Q_CHAIN, s2, s2, s1, -1.0, R12, R12, 1.0, W22, CAPITAL_GEMM_C_UPPER | GEMM_TRAILING));
   }
   if (complete) {
     // inverse combine, first half (cholinv.hpp:151): T^T = R12^T Rinv11^T  (B = RiT11, lower triangular) -- nobody needs it before

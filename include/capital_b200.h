@@ -183,6 +183,19 @@ enum {
 capital_status_t capital_blas_gemm_tn_f64(capital_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha,
                                           const double* A, int64_t lda, const double* B, int64_t ldb,
                                           double beta, double* C, int64_t ldc, int flags);
+/* EXPERIMENTAL, OFF BY DEFAULT -- BASELINE config 5 ("FP32/TF32 Cholesky, mixed-precision trailing update with FP64 panel").
+ * The reference has no float BLAS path (src/blas/interface.hpp:43-97 is double only): this is an extension of the blas::engine seam,
+ * not a replacement of a reference entry point.  capital_blas_gemm_tn_tf32: the product of capital_blas_gemm_tn_f64 (FP64 operands
+ * and result, only the CAPITAL_GEMM_C_UPPER flag) computed on the TF32 tensor cores (tcgen05.mma.kind::tf32, accumulator in TMEM);
+ * passes = 1: operands rounded to TF32 (relative error ~ 5e-4 per product), passes = 3: operands split hi + lo (FP32-class).
+ * capital_set_trailing_precision(ctx, 0 | 1 | 3): cholinv::factor runs its trailing updates A22 -= R12^T R12 (cholinv.hpp:131-134,
+ * summa::syrk) in that mode; base cases, R12, the inverse and every other product stay FP64.  Single GPU and c = 1 grids.
+ * capital_tf32_stats: launches / flops of the TF32 kernel since capital_create. */
+capital_status_t capital_blas_gemm_tn_tf32(capital_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
+                                           const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags, int passes);
+capital_status_t capital_set_trailing_precision(capital_ctx* ctx, int mode);
+capital_status_t capital_tf32_stats(const capital_ctx* ctx, int64_t* launches, double* flops);
+
 /* lapack::engine::_potrf('U') + _trtri('U','N') fused (lapack/interface.hpp:30-58; called back to
  * back at cholinv/policy.h:199-201): A (n x n, upper read) -> R, Rinv upper (lower zeroed). DEVICE pointers. */
 capital_status_t capital_lapack_potrf_trtri_f64(capital_ctx* ctx, int64_t n, const double* A, int64_t lda,

@@ -1,0 +1,49 @@
+"""EXPERIMENTAL mixed-precision path (BASELINE config 5): trailing updates on the TF32 tensor cores (tcgen05 + TMEM,
+capital_b200/csrc/gemm_tf32.cu), FP64 everywhere else.  Off by default in the library.
+
+The kernel was written after the round's GPU budget was spent: it assembles for sm_100a (UTCHMMA / LDTM / UTMALDG in the SASS) but the
+run of THIS file is its first execution.  Hence: (1) the file sorts last, (2) every case runs in a child process with its own CUDA
+context and a timeout (the kernel's mbarrier waits are bounded too), (3) the cases are xfail(strict=False) -- an XPASS in the report
+means the path computed the right numbers on this device, an XFAIL that it did not; neither touches the FP64 product path.
+Gates (no reference float path exists, src/blas/interface.hpp:43-97: the FP64 results are the yardstick):
+  product:       |C - C_fp64| / max(|A|^T |B|) <= 5e-4 (TF32 operands) / 2e-6 (split operands, 3 passes)
+  factorization: residual ||A - R^T R||_F / ||A||_F <= 1e-6 (TF32) / 1e-8 (3 x TF32) at n = 4096 (CPU emulation of the rounding:
+                 5e-9 / 1e-10), and > 1e-13 with the TF32 kernel's launch counter > 0 -- i.e. the tensor-core path really ran."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+WHY = "TF32 tcgen05 path: written without GPU access, this run is its first execution (XPASS = it works)"
+
+
+def worker(*args, timeout=600):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "tf32_worker.py"), *map(str, args)], capture_output=True, text=True,
+                       timeout=timeout)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+@pytest.mark.xfail(strict=False, reason=WHY)
+def test_tf32_product_against_fp64():
+    out = worker("gemm")["gemm"]
+    for c in out:
+        assert c["status"] == 0, c
+        assert c["padding_untouched"], c
+        assert c["rel_err"] <= (5e-4 if c["passes"] == 1 else 2e-6), c
+    # and the tensor cores were really used: TF32 rounding leaves a visible error on a long contraction
+    assert any(c["passes"] == 1 and c["rel_err"] > 1e-9 for c in out)
+
+
+@pytest.mark.xfail(strict=False, reason=WHY)
+def test_cholinv_mixed_precision_trailing_update():
+    d = worker("cholinv", 4096, -3)
+    assert d["tf32_launches"]["f64"] == 0 and d["tf32_launches"]["tf32"] > 0 and d["tf32_launches"]["tf32x3"] > 0
+    assert d["residual"]["f64"] <= 1e-14
+    assert 1e-13 < d["residual"]["tf32"] <= 1e-6
+    assert d["residual"]["tf32x3"] <= 1e-8
+    assert d["R_rel_diff"]["tf32"] <= 1e-4 and d["R_rel_diff"]["tf32x3"] <= 1e-6
