@@ -71,7 +71,7 @@ __device__ __forceinline__ bool mbar_wait_bounded(uint32_t bar, uint32_t parity,
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       if (t0 == 0) t0 = t;
-      else if (t - t0 > 2000000000ull) { atomicExch(err, -3); return false; }
+      else if (t - t0 > 2000000000ull || *(volatile int*)err == -3) { atomicExch(err, -3); return false; }
     }
   }
 }
@@ -85,10 +85,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), K-major operand, 128-byte swizzle: start address >> 4 @ [0,14),
-// leading byte offset unused (one swizzle atom along K), stride byte offset = 8 rows x 128 B = 1024 (>> 4) @ [32,46), version 1 @ 46,
+// leading byte offset @ [16,30) (not used by the hardware for a swizzled K-major operand with one atom along K; 1 as
+// cute::UMMA::make_umma_desc<Major::K> sets it), stride byte offset = 8 rows x 128 B = 1024 (>> 4) @ [32,46), version 1 @ 46,
 // layout SWIZZLE_128B = 2 @ [61,64).  Tiles are 1024-byte aligned (base_offset 0).
 __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -108,6 +109,8 @@ __global__ void __launch_bounds__(128, 1) gemm_tn_tf32_kernel(const __grid_const
   const int tm = blockIdx.x, tn = blockIdx.y;
   const int m0 = tm * TBM, n0 = tn * TBN;
   if ((p.flags & CAPITAL_GEMM_C_UPPER) && m0 > n0 + p.noff + TBN - 1) return;  // tile strictly below the diagonal (whole CTA)
+  // an earlier CTA's watchdog fired: the launch is lost, do not spend 2 s per remaining tile (block-uniform decision)
+  if (__syncthreads_or(*(volatile int*)p.err == -3)) return;
   const int nk = (p.K + TBK - 1) / TBK;
   const int niter = nk * p.npair;
 
