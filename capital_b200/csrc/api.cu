@@ -350,7 +350,7 @@ capital_status_t capital_create(capital_ctx** out, const capital_grid_t* grid, i
   ok = ok && cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn != nullptr;
   if (!ok) { capital_destroy(ctx); return CAPITAL_ERR_CUDA; }
   ctx->encode = (cuTensorMapEncodeTiled_fn)fn;
-  if (gemm_tn_init(ctx) != CAPITAL_OK || leaf_init(ctx) != CAPITAL_OK || gemm_tf32_init(ctx) != CAPITAL_OK) { capital_destroy(ctx); return CAPITAL_ERR_CUDA; }
+  if (gemm_tn_init(ctx) != CAPITAL_OK || leaf_init(ctx) != CAPITAL_OK) { capital_destroy(ctx); return CAPITAL_ERR_CUDA; }
   if (const char* e = getenv("CAPITAL_TF32_MIN_K")) ctx->tf32_min_k = atoll(e);
   if (const char* e = getenv("CAPITAL_KCHUNK")) ctx->kchunk = atoll(e);
   if (const char* e = getenv("CAPITAL_FAR_MIN")) ctx->far_min = atoll(e);

@@ -83,6 +83,7 @@ struct capital_ctx {
   // EXPERIMENTAL, off by default (capital_set_trailing_precision): trailing updates A22 -= R12^T R12 on the TF32 tensor cores
   // (gemm_tf32.cu); 0 = FP64 DMMA, 1 = TF32, 3 = 3 x TF32 with split operands.  Products with k below tf32_min_k stay FP64.
   int trailing_mode = 0;
+  bool tf32_ready = false;  // the TF32 kernel's attributes are set at its first use, never by the default FP64 path
   int64_t tf32_min_k = 256;
   int64_t tf32_launches = 0;
   double tf32_flops = 0.0;

@@ -268,6 +268,10 @@ capital_status_t gemm_tn_tf32_x(capital_ctx* ctx, cudaStream_t st, int64_t m, in
     ctx->set_error("gemm_tn_tf32: unsupported arguments (passes 1 or 3, only the C_UPPER structure flag)");
     return CAPITAL_ERR_INVALID;
   }
+  if (!ctx->tf32_ready) {
+    CAP_TRY(gemm_tf32_init(ctx));
+    ctx->tf32_ready = true;
+  }
   const std::string tag = stream_tag(ctx, st);
   const int64_t ldf = round_up(k, 4);  // 16-byte rows for TMA
   Tf32Maps maps;
