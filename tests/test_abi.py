@@ -60,6 +60,15 @@ def test_peer_wait_mode_without_a_clique():
     assert _lib.lib().capital_peer_wait_mode(None) == -1
 
 
+def test_experimental_tf32_entry_points_reject_a_null_context():
+    import ctypes as C
+    L = _lib.lib()
+    n, f = C.c_int64(), C.c_double()
+    assert L.capital_set_trailing_precision(None, 1) == _lib.ERR_INVALID
+    assert L.capital_tf32_stats(None, C.byref(n), C.byref(f)) == _lib.ERR_INVALID
+    assert L.capital_blas_gemm_tn_tf32(None, 1, 1, 1, 1.0, None, 1, None, 1, 0.0, None, 1, 0, 1) == _lib.ERR_INVALID
+
+
 def test_create_fails_loudly_without_device():
     import torch
     if torch.cuda.is_available():
