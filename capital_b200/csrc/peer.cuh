@@ -4,8 +4,10 @@
 // cudaMalloc'ed, exported with cudaIpcGetMemHandle and mapped by every other rank, so that any rank can
 //   * DMA a finished block into a consumer's mirror buffer (copy engines, cudaMemcpy2DAsync on a push stream),
 //   * store GEMM partials / final tiles straight from the epilogue into a depth partner's memory (gemm_tn.cu, GemmXDev),
-//   * raise a flag in another rank's control block and wait on its own flags -- stream memory operations
-//     (cuStreamWriteValue64 / cuStreamWaitValue64: no SM is needed, so a flag is never stuck behind the CTAs of a running GEMM).
+//   * raise a flag in another rank's control block -- a stream memory operation (cuStreamWriteValue64: no SM is needed, so a flag
+//     is never stuck behind the CTAs of a running GEMM) -- and wait on its own flags: a flushed memory-operation wait where the device
+//     can flush remote writes, else a one-warp kernel spinning on ld.acquire.sys (peer_init; an unflushed memory-op wait does not
+//     make the peer's earlier stores visible to the kernels behind it).
 // The arena layout is a pure function of the problem shape and of the grid, identical on every rank, so an offset computed
 // locally addresses the same object in every peer's arena ("symmetric heap").  Flags carry monotonically increasing sequence
 // numbers (never reset), which makes "wait until flag >= v" race-free across repeated factorizations.
