@@ -412,6 +412,42 @@ def ours(args):
         except Exception as ex:  # noqa
             cacqr = {"error": repr(ex)[:300]}
 
+    # ---- the same two records with the OTHER flag-wait flavour (same box, same context; nothing above depends on it) ----
+    # Default: acquire-spin wait kernels (or flushed memory-op waits where the device can flush).  "memop" = unflushed
+    # cuStreamWaitValue64, what the round-2 profiles were measured with and what showed 1e-10-level residuals at n = 32768 over
+    # NVLink.  Timing and residual of both, side by side.
+    wait_modes = None
+    if world > 1 and not args.no_extra and not args.n:
+        mode0 = ctx.peer_wait_mode()
+        try:
+            other = "memop" if mode0 != "memop" else "kernel"
+            ctx.set_peer_wait_mode(other)
+            wait_modes = {"default": mode0, "other": other}
+            for label, nn, bb in (("headline", n, bcm), ("strong", STRONG_N, STRONG_BCM[world])):
+                Aa = cb.matrix(nn, nn, dgrid, dgrid).distribute_symmetric(topo)
+                pp = cb.cholinv.info(0, 1, bb, "U")
+                for _ in range(2):
+                    cb.cholinv.factor(Aa, pp, topo)
+                barrier()
+                e0.record()
+                for _ in range(3):
+                    cb.cholinv.factor(Aa, pp, topo)
+                e1.record()
+                barrier()
+                ms_o = reduce_max(e0.elapsed_time(e1)) / 3
+                wait_modes[label + "_with_other"] = {"n": nn, "ms_per_step": ms_o, "tflops": nn ** 3 / 3 / (ms_o * 1e-3) / 1e12,
+                                                     "residual": cb.cholinv.residual(Aa, pp, topo), "steps": 3}
+                del Aa, pp
+                ctx.release_workspace()
+                torch.cuda.empty_cache()
+        except Exception as ex:  # noqa
+            wait_modes = {"default": mode0, "error": repr(ex)[:300]}
+        finally:
+            try:
+                ctx.set_peer_wait_mode(mode0)
+            except Exception:  # noqa
+                pass
+
     # ---- EXPERIMENTAL (BASELINE config 5, off by default in the library): trailing updates on the TF32 tensor cores ----
     # Child process: the tcgen05 kernel was written without GPU access and has its own CUDA context here, so that nothing it does can
     # touch the numbers above.  Single GPU only in the bench; the c = 1 grids take the same path through dist.cu.
@@ -475,6 +511,8 @@ def ours(args):
             out["strong"] = strong
         if tf32 is not None:
             out["mixed_precision_tf32"] = tf32
+        if wait_modes is not None:
+            out["flag_wait_modes"] = wait_modes
         if cacqr is not None:
             out["cacqr"] = cacqr
         if world == 1 and not args.no_cpu:

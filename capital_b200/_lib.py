@@ -13,7 +13,7 @@ GEMM_A_UPPER, GEMM_A_LOWER, GEMM_B_UPPER, GEMM_B_LOWER, GEMM_C_UPPER = 1, 2, 4, 
 
 EXPORTS = [  # every symbol include/capital_b200.h declares
     "capital_grid_square", "capital_grid_rect", "capital_cholinv_bc_dimension", "capital_create",
-    "capital_comm_unique_id", "capital_comm_init", "capital_comm_init_host", "capital_peer_wait_mode", "capital_dist_trace_cholinv", "capital_destroy", "capital_last_error", "capital_get_counters",
+    "capital_comm_unique_id", "capital_comm_init", "capital_comm_init_host", "capital_peer_wait_mode", "capital_set_peer_wait_mode", "capital_dist_trace_cholinv", "capital_destroy", "capital_last_error", "capital_get_counters",
     "capital_reset_counters", "capital_synchronize", "capital_set_stream", "capital_release_workspace", "capital_last_factor_ms", "capital_profile_begin", "capital_profile_end", "capital_probe_dmma_f64", "capital_blas_gemm_tn_tf32", "capital_set_trailing_precision", "capital_tf32_stats", "capital_timeline_begin", "capital_timeline_end", "capital_set_overlap", "capital_distribute_symmetric_f64",
     "capital_distribute_random_f64", "capital_cholinv_factor_f64", "capital_cholinv_residual_f64",
     "capital_cacqr_factor_f64", "capital_cacqr_residual_f64", "capital_summa_gemm_tn_f64", "capital_blas_gemm_tn_f64",
@@ -67,6 +67,7 @@ def lib() -> C.CDLL:
     L.capital_tf32_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(dbl)]
     L.capital_peer_wait_mode.argtypes = [vp]
     L.capital_peer_wait_mode.restype = C.c_int
+    L.capital_set_peer_wait_mode.argtypes = [vp, ci]
     L.capital_dist_trace_cholinv.argtypes = [C.POINTER(Grid), i64, C.POINTER(CholinvArgs), C.POINTER(i64), i64, C.POINTER(i64)]
     L.capital_destroy.argtypes = [vp]
     L.capital_destroy.restype = None
@@ -145,6 +146,10 @@ class Context:
     def peer_wait_mode(self) -> str:
         """how this rank's streams wait for a peer-written flag (capital_peer_wait_mode)"""
         return {-1: "none", 0: "memop", 1: "memop+flush", 2: "kernel"}[lib().capital_peer_wait_mode(self._h)]
+
+    def set_peer_wait_mode(self, name: str):
+        """'memop' | 'memop+flush' | 'kernel' -- between calls only"""
+        self.check(lib().capital_set_peer_wait_mode(self._h, {"memop": 0, "memop+flush": 1, "kernel": 2}[name]))
 
     def release_workspace(self):
         """policy::cholinv::FlushIntermediates: free every work buffer (re-allocated by the next call)."""

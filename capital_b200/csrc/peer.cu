@@ -183,6 +183,7 @@ capital_status_t peer_init(capital_ctx* ctx, peer_allgather_fn ag, void* user) {
       CAP_CUDA(cudaStreamCreateWithFlags(&ts, cudaStreamNonBlocking));
       const bool ok = memops_issue(ctx, ts, t, true, true) == CAPITAL_OK && cudaStreamSynchronize(ts) == cudaSuccess;
       cudaStreamDestroy(ts);
+      P->can_flush = ok;
       if (ok) P->wait_mode = PEER_WAIT_MEMOP_FLUSH;
       else { cudaGetLastError(); ctx->set_error(""); }
     }
@@ -363,6 +364,17 @@ extern "C" capital_status_t capital_comm_init(capital_ctx* ctx, const void* uid)
 extern "C" int capital_peer_wait_mode(const capital_ctx* ctx) {
   if (!ctx || !ctx->peer) return -1;
   return ((const Peer*)ctx->peer)->wait_mode;
+}
+
+// between calls only (every stream of the context idle): waits enqueued afterwards use the new flavour
+extern "C" capital_status_t capital_set_peer_wait_mode(capital_ctx* ctx, int mode) {
+  if (!ctx || !ctx->peer) return CAPITAL_ERR_INVALID;
+  Peer* P = (Peer*)ctx->peer;
+  if (mode == PEER_WAIT_KERNEL) { P->wait_mode = mode; return CAPITAL_OK; }
+  if (mode == PEER_WAIT_MEMOP && P->memops) { P->wait_mode = mode; return CAPITAL_OK; }
+  if (mode == PEER_WAIT_MEMOP_FLUSH && P->memops && P->can_flush) { P->wait_mode = mode; return CAPITAL_OK; }
+  ctx->set_error("peer wait mode: 0 (memory op), 1 (flushed memory op; needs device support) or 2 (acquire-spin kernel)");
+  return CAPITAL_ERR_UNSUPPORTED;
 }
 
 extern "C" capital_status_t capital_comm_init_host(capital_ctx* ctx, capital_allgather_fn allgather, void* user) {

@@ -55,6 +55,7 @@ struct Peer {
   unsigned long long push_id[PEER_Q] = {};          // logical push events issued so far (same on every rank)
   unsigned long long prod_seq[PEER_QC] = {};        // products with a depth exchange issued so far
   unsigned long long bar_epoch = 0, ar_epoch = 0;
+  bool can_flush = false;  // the device accepts CU_STREAM_WAIT_VALUE_FLUSH (attribute + self test at init)
   int wait_mode = 2;    // PEER_WAIT_*: how a stream waits for a peer-written flag [env CAPITAL_PEER_WAIT]
   bool memops = true;   // flags through stream memory operations (no SM needed) instead of one-warp kernels [env CAPITAL_PEER_MEMOPS]
   // NCCL bootstrap (only when capital_comm_init was used)

@@ -91,6 +91,9 @@ capital_status_t capital_comm_init_host(capital_ctx* ctx, capital_allgather_fn a
  * of outstanding remote writes (CU_STREAM_WAIT_VALUE_FLUSH; the default where the device supports it), 2 = one-warp kernel spinning
  * on ld.acquire.sys, -1 = the context has not joined a clique.  Override: env CAPITAL_PEER_WAIT = memop | flush | kernel. */
 int capital_peer_wait_mode(const capital_ctx* ctx);
+/* Switch the wait flavour between calls (measurement: bench.py times both on the same box).  CAPITAL_ERR_UNSUPPORTED when the device
+ * cannot do it (mode 1 without flush support). */
+capital_status_t capital_set_peer_wait_mode(capital_ctx* ctx, int mode);
 void capital_destroy(capital_ctx* ctx);
 const char* capital_last_error(const capital_ctx* ctx);
 capital_status_t capital_get_counters(const capital_ctx* ctx, capital_counters_t* out);
