@@ -166,6 +166,7 @@ def main():
     res, orth = cb.cacqr.validate(A, qa, qt)
     ok &= res < 1e-13 and orth < 1e-14
     msgs.append(f"cacqr m={m} n={n} P={world}: res={res:.1e} orth={orth:.1e}")
+    msgs.append(f"peer flag waits: {qt.context().peer_wait_mode()}")
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)
     if rank == 0:
