@@ -166,6 +166,10 @@ def parity_block(cb, torch, np, world, rank, c):
         qa = cb.cacqr.info(2, cb.cholinv.info(1, 1, -1, "U"))
         cb.cacqr.factor(A, qa, t3)
         worst = max(worst, float(np.abs(qa.Q.cpu().numpy() - z[f"Q_{rank}"]).max())); cases.append("cacqr_p8_3d_m256_n64")
+        meta, z = load("cacqr_p8_3d_m256_n64_ci0")  # complete_inv = 0: the reference's block `solve` path (cacqr.hpp:46-71)
+        qa = cb.cacqr.info(2, cb.cholinv.info(0, 1, -1, "U"))
+        cb.cacqr.factor(A, qa, t3)
+        worst = max(worst, float(np.abs(qa.Q.cpu().numpy() - z[f"Q_{rank}"]).max())); cases.append("cacqr_p8_3d_m256_n64_ci0")
         qt = cb.topo.rect(8, rank, 1)
         meta, z = load("cacqr_p8_1d_m1024_n32")
         A = cb.matrix(meta["n"], meta["m"], 1, 8).distribute_random(qt, rank)

@@ -23,6 +23,7 @@ CACQR = [  # name, P, variant, m, n, c, complete_inv, split, bc_mult
     ("cacqr_p1_m512_n32", 1, 2, 512, 32, 1, 0, 1, 0),
     ("cacqr_p8_1d_m1024_n32", 8, 2, 1024, 32, 1, 0, 1, 0),
     ("cacqr_p8_3d_m256_n64", 8, 2, 256, 64, 2, 1, 1, -1),
+    ("cacqr_p8_3d_m256_n64_ci0", 8, 2, 256, 64, 2, 0, 1, -1),  # complete_inv = 0: the reference's block `solve` (cacqr.hpp:46-71)
 ]
 
 def run(cmd, np_):
@@ -31,7 +32,10 @@ def run(cmd, np_):
     return json.loads(out.strip().splitlines()[-1])
 
 def main():
+    only = set(sys.argv[1:])  # optional: regenerate the named fixtures only
     for name, P, n, ci, split, bcm, pol in CHOLINV:
+        if only and name not in only:
+            continue
         with tempfile.TemporaryDirectory() as td:
             meta = run([os.path.join(REF, "ref_cholinv"), str(n), str(ci), str(split), str(bcm), str(pol), "1", os.path.join(td, "d")], P)
             arrs = {}
@@ -41,6 +45,8 @@ def main():
             np.savez_compressed(os.path.join(HERE, name + ".npz"), meta=json.dumps(meta), **arrs)
             print(name, meta)
     for name, P, var, m, n, c, ci, split, bcm in CACQR:
+        if only and name not in only:
+            continue
         with tempfile.TemporaryDirectory() as td:
             meta = run([os.path.join(REF, "ref_cacqr"), str(var), str(m), str(n), str(c), str(ci), str(split), str(bcm), "1", os.path.join(td, "d")], P)
             arrs = {}

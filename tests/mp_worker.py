@@ -145,6 +145,14 @@ def main():
         res, orth = cb.cacqr.validate(A, qa, t3)
         ok &= eq < 1e-12 and res < 1e-14 and orth < 1e-15
         msgs.append(f"cacqr 3D golden: dQ={eq:.1e} res={res:.1e} orth={orth:.1e}")
+        # complete_inv = 0: the reference takes its block `solve` (cacqr.hpp:46-71); here the complete inverse is applied -- same Q
+        meta, z = load("cacqr_p8_3d_m256_n64_ci0")
+        qa0 = cb.cacqr.info(2, cb.cholinv.info(0, 1, -1, "U"))
+        cb.cacqr.factor(A, qa0, t3)
+        eq0 = np.abs(qa0.Q.cpu().numpy() - z[f"Q_{rank}"]).max()
+        res0, orth0 = cb.cacqr.validate(A, qa0, t3)
+        ok &= eq0 < 1e-12 and res0 < 1e-14 and orth0 < 1e-15
+        msgs.append(f"cacqr 3D golden (complete_inv=0, reference `solve`): dQ={eq0:.1e} res={res0:.1e}")
     # --- 1D CholeskyQR2 on all ranks ---
     qt = cb.topo.rect(world, rank, 1)
     if world == 8:

@@ -108,3 +108,16 @@ def test_topology_and_layout_helpers():
     assert np.array_equal(co.cyclic_assemble(blocks, 5, 7, 3, 2), a)
     u = np.triu(np.arange(16.0).reshape(4, 4))
     assert np.array_equal(co.unpack_upper(co.pack_upper(u), 4), u)
+
+
+def test_reference_solve_path_yields_the_same_q():
+    """cacqr::solve (complete_inv = 0, cacqr.hpp:46-71: block forward substitution with the two diagonal inverse blocks) against the
+    reference's own complete_inv = 1 run on the same input: Q agrees to rounding, so applying the complete inverse -- what
+    capital_b200's 3D sweep always does (dist.cu) -- is within tolerance of BOTH reference paths.  The multi-GPU tests compare the
+    GPU result against each dump."""
+    (m0, z0), (_, z1) = load("cacqr_p8_3d_m256_n64_ci0"), load("cacqr_p8_3d_m256_n64")
+    assert m0["residual"] < 1e-14 and m0["orthogonality"] < 1e-15
+    for r in range(8):
+        assert np.array_equal(z0[f"A_{r}"], z1[f"A_{r}"])
+        assert np.abs(z0[f"Q_{r}"] - z1[f"Q_{r}"]).max() < 1e-15
+        assert np.abs(z0[f"R_{r}"] - z1[f"R_{r}"]).max() <= 1e-13 * np.abs(z1[f"R_{r}"]).max()
