@@ -18,6 +18,8 @@ CHOLINV = [  # name, P, n, complete_inv, split, bc_mult, policy
     ("cholinv_p1_n128_ci0", 1, 128, 0, 1, -3, 2),
     ("cholinv_p8_n128_ci0", 8, 128, 0, 1, -1, 0),
     ("cholinv_p8_n192_ci1", 8, 192, 1, 1, -2, 0),
+    ("cholinv_p1_n128_ci0_split2", 1, 128, 0, 2, -3, 0),  # split = 2: the left child is a quarter (cholinv.hpp:92,107)
+    ("cholinv_p8_n256_ci1_split2", 8, 256, 1, 2, -2, 0),
 ]
 CACQR = [  # name, P, variant, m, n, c, complete_inv, split, bc_mult
     ("cacqr_p1_m512_n32", 1, 2, 512, 32, 1, 0, 1, 0),

@@ -20,9 +20,9 @@ T_WAIT, T_SIGNAL, T_PRODUCT, T_EVREC, T_EVWAIT, T_DMA, T_KERNEL, T_READ, T_WRITE
 NSTREAM = 12
 
 
-def trace(size, rank, c, n, ci, bcm):
+def trace(size, rank, c, n, ci, bcm, split=1):
     g = cb.topo.square(size, rank, c).grid
-    args = _lib.CholinvArgs(ci, 1, bcm, b"U")
+    args = _lib.CholinvArgs(ci, split, bcm, b"U")
     cnt = C.c_int64()
     L = _lib.lib()
     st = L.capital_dist_trace_cholinv(C.byref(g), n, C.byref(args), None, 0, C.byref(cnt))
@@ -193,6 +193,19 @@ def test_flag_protocol_is_deadlock_free_and_race_free(size, n, ci, bcm, monkeypa
         assert (kinds == T_DMA).sum() > 0 and (kinds == T_WAIT).sum() > 0
     bad = rp.races()
     assert not bad, f"{len(bad)} unordered conflicting accesses, e.g. {bad[:3]}"
+
+
+@pytest.mark.parametrize("size,n,ci", [(8, 2048, 1), (8, 2048, 0), (4, 2048, 1), (2, 1024, 0)])
+def test_uneven_split_is_clean_too(size, n, ci, monkeypatch):
+    """split = 2 (cholinv.hpp:92,107: the left child gets a quarter): node sizes stop being powers of two, every window offset changes"""
+    monkeypatch.setenv("CAPITAL_DIST_FAR_MIN", "64")
+    monkeypatch.setenv("CAPITAL_DIST_SIDE_MIN", "32")
+    monkeypatch.setenv("CAPITAL_DIST_CHUNK_MIN", "256")
+    c, d = GRIDS[size]
+    traces = [trace(size, r, c, n, ci, -3, split=2) for r in range(size)]
+    rp = Replay(traces)
+    assert not rp.run((c, d))
+    assert not rp.races()
 
 
 def test_pipelined_chunked_products_are_clean_too(monkeypatch):

@@ -47,3 +47,33 @@ def test_cholinv_mixed_precision_trailing_update():
     assert 1e-13 < d["residual"]["tf32"] <= 1e-6
     assert d["residual"]["tf32x3"] <= 1e-8
     assert d["R_rel_diff"]["tf32"] <= 1e-4 and d["R_rel_diff"]["tf32x3"] <= 1e-6
+
+
+# ---- not TF32: a parameter of the FP64 path whose first GPU run is this file too (kept here so that it cannot stop the suite early) ----
+def test_cholinv_uneven_split_matches_reference_dump_and_oracle():
+    """split = 2 (cholinv.hpp:92,107: the left child gets a quarter of the node): the reference's own dump, elementwise, and the numpy
+    restatement (pinned to that dump on CPU) at a ragged size."""
+    import numpy as np
+    import capital_b200 as cb
+    from oracle import capital_oracle as co
+    topo = cb.topo.square(1, 0, 1)
+    z = np.load(os.path.join(ROOT, "tests", "golden", "cholinv_p1_n128_ci0_split2.npz"))
+    meta = json.loads(str(z["meta"]))
+    n = meta["n"]
+    A = cb.matrix(n, n, 1, 1).distribute_symmetric(topo)
+    args = cb.cholinv.info(meta["complete_inv"], meta["split"], meta["bc_mult_dim"], "U")
+    cb.cholinv.factor(A, args, topo)
+    r, ri = args.R.cpu().numpy(), args.Rinv.cpu().numpy()
+    assert np.abs(r - z["R_0"]).max() <= 1e-13 * np.abs(z["R_0"]).max()
+    assert np.abs(ri - z["Rinv_0"]).max() <= 1e-13 * np.abs(z["Rinv_0"]).max()
+    assert np.array_equal(ri == 0, z["Rinv_0"] == 0)  # the skipped block sits at n >> 2 now (cholinv.hpp:147)
+    for n, ci, bcm in ((1000, 0, -3), (2048, 1, -3)):
+        A = cb.matrix(n, n, 1, 1).distribute_symmetric(topo)
+        args = cb.cholinv.info(ci, 2, bcm, "U", serialize=False)
+        cb.cholinv.factor(A, args, topo)
+        a = co.spd_global(n)
+        r_o, ri_o = co.cholinv(a, bool(ci), 2, co.bc_dimension(n, 1, 1, bcm))
+        R, Ri = cb.cholinv.construct_R(args).cpu().numpy(), cb.cholinv.construct_Rinv(args).cpu().numpy()
+        assert np.abs(R - r_o).max() <= 2e-13 * np.abs(r_o).max()
+        assert np.abs(Ri - ri_o).max() <= 2e-13 * np.abs(ri_o).max()
+        assert cb.cholinv.residual(A, args, topo) <= 1e-12

@@ -22,7 +22,8 @@ def test_drand48_known_answers():
     assert np.allclose(a, a.T) and abs(a[0, 0] - 8.170828036106290) < 1e-12
 
 
-@pytest.mark.parametrize("name", ["cholinv_p1_n96_ci1", "cholinv_p1_n128_ci0", "cholinv_p8_n128_ci0", "cholinv_p8_n192_ci1"])
+@pytest.mark.parametrize("name", ["cholinv_p1_n96_ci1", "cholinv_p1_n128_ci0", "cholinv_p8_n128_ci0", "cholinv_p8_n192_ci1",
+                                  "cholinv_p1_n128_ci0_split2", "cholinv_p8_n256_ci1_split2"])
 def test_generator_and_cholinv_match_reference(name):
     meta, z = load(name)
     n, P, c, d = meta["n"], meta["P"], meta["c"], meta["d"]
