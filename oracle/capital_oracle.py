@@ -256,6 +256,38 @@ def cacqr_1d(blocks: list, num_iter: int = 2):
     return qs, r1
 
 
+# --------------------------------------------------------------------------------------------------
+# CA-CholeskyQR2 on the 3D grid, c == d  (src/alg/qr/cacqr/cacqr.hpp:75-120,195-215; solve: :46-71)
+# --------------------------------------------------------------------------------------------------
+def cacqr_3d(a: np.ndarray, c: int, num_iter: int, complete_inv: bool, split: int, bc_mult_dim: int):
+    """Global-view restatement of invoke_3d / sweep_3d for an m x n matrix on a c x c x c grid.  Per sweep: Gram matrix G = Q^T Q
+    (row Bcast + gemm + column Reduce + depth Bcast, :92-99), cholinv::factor on G over the same grid (:103), then either
+    Q <- Q R^-1 (complete_inv, summa trmm Right/Upper, :106-111) or the block `solve` (:46-71): with n1 = (localN >> split) * c,
+    Q1 <- Q1 Rinv11, Q2 <- (Q2 - Q1 R12) Rinv22 -- which needs only the two diagonal blocks of the inverse, the ones
+    complete_inv = 0 leaves cholinv to compute.  Two sweeps: R = R2 R1 (:203-209).  Returns (Q, R)."""
+    n = a.shape[1]
+    q = np.array(a, dtype=np.float64)
+    bc = bc_dimension(local_dim(n, c), c, c, bc_mult_dim)
+
+    def sweep():
+        g = q.T @ q
+        r, ri = cholinv(g, complete_inv, split, bc, c)
+        if complete_inv:
+            q[...] = q @ ri
+        else:
+            n1 = (local_dim(n, c) >> split) * c
+            q1 = q[:, :n1] @ ri[:n1, :n1]
+            q[:, n1:] = (q[:, n1:] - q1 @ r[:n1, n1:]) @ ri[n1:, n1:]
+            q[:, :n1] = q1
+        return r
+
+    r1 = sweep()
+    if num_iter > 1:
+        r2 = sweep()
+        return q, np.triu(r2 @ r1)
+    return q, r1
+
+
 def qr_residual(a: np.ndarray, q: np.ndarray, r: np.ndarray) -> float:
     """test/qr/validate.hpp:37-52: ||QR - A||_F / ||A||_F."""
     return float(np.linalg.norm(q @ r - a) / np.linalg.norm(a))
