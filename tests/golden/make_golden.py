@@ -25,7 +25,8 @@ CACQR = [  # name, P, variant, m, n, c, complete_inv, split, bc_mult
     ("cacqr_p1_m512_n32", 1, 2, 512, 32, 1, 0, 1, 0),
     ("cacqr_p8_1d_m1024_n32", 8, 2, 1024, 32, 1, 0, 1, 0),
     ("cacqr_p8_3d_m256_n64", 8, 2, 256, 64, 2, 1, 1, -1),
-    ("cacqr_p8_3d_m256_n64_ci0", 8, 2, 256, 64, 2, 0, 1, -1),  # complete_inv = 0: the reference's block `solve` (cacqr.hpp:46-71)
+    ("cacqr_p8_3d_m256_n64_ci0", 8, 2, 256, 64, 2, 0, 1, -1),
+    ("cacqr_p8_1d_m1024_n32_it1", 8, 1, 1024, 32, 1, 0, 1, 0),  # num_iter = 1: one sweep (CholeskyQR, not QR2)  # complete_inv = 0: the reference's block `solve` (cacqr.hpp:46-71)
 ]
 
 def run(cmd, np_):

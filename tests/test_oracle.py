@@ -60,7 +60,7 @@ def test_cholinv_vs_lapack_and_incomplete_inverse():
     assert np.all(ri0[:h, h:] == 0) and np.array_equal(ri0[:h, :h], ri[:h, :h]) and np.array_equal(ri0[h:, h:], ri[h:, h:])
 
 
-@pytest.mark.parametrize("name", ["cacqr_p1_m512_n32", "cacqr_p8_1d_m1024_n32"])
+@pytest.mark.parametrize("name", ["cacqr_p1_m512_n32", "cacqr_p8_1d_m1024_n32", "cacqr_p8_1d_m1024_n32_it1"])
 def test_cacqr_1d_matches_reference(name):
     meta, z = load(name)
     m, n, P, c, d = meta["m"], meta["n"], meta["P"], meta["c"], meta["d"]
@@ -71,12 +71,20 @@ def test_cacqr_1d_matches_reference(name):
         loc = co.random_local(m, n, c, d, t["x"], t["y"], rank // c)
         assert np.array_equal(z[f"A_{rank}"].reshape(lr, n, order="F"), loc)  # generator bit-exact
         blocks.append(loc)
-    qs, r = co.cacqr_1d(blocks, 2)
+    qs, r = co.cacqr_1d(blocks, meta["variant"])  # the driver's `variant` is num_iter (cacqr.h info::num_iter)
     a = co.cyclic_assemble({(0, y): blocks[y] for y in range(P)}, m, n, 1, d)
     q = co.cyclic_assemble({(0, y): qs[y] for y in range(P)}, m, n, 1, d)
-    assert co.qr_residual(a, q, r) < 1e-14 and co.qr_orthogonality(q) < 1e-15
+    # one sweep (CholeskyQR) loses orthogonality with cond(A)^2 eps; two sweeps recover it
+    assert co.qr_residual(a, q, r) < 1e-14 and co.qr_orthogonality(q) < (1e-15 if meta["variant"] > 1 else 1e-13)
     for rank in range(P):
-        assert np.abs(co.unpack_upper(z[f"R_{rank}"], n) - r).max() < 1e-12 * np.abs(r).max()
+        if meta["variant"] > 1:
+            assert np.abs(co.unpack_upper(z[f"R_{rank}"], n) - r).max() < 1e-12 * np.abs(r).max()
+        else:
+            # reference quirk: with num_iter = 1 invoke_1d never finalises R (SP::complete_1d sits in the num_iter > 1 branch,
+            # cacqr.hpp:180-188) -- args.R comes back holding the Gram matrix (its own validator reads a residual of 65).  Q is right.
+            g = np.triu(a.T @ a)
+            assert np.abs(co.unpack_upper(z[f"R_{rank}"], n) - g).max() < 1e-12 * np.abs(g).max()
+            assert meta["residual"] > 1.0
         assert np.abs(z[f"Q_{rank}"].reshape(lr, n, order="F") - qs[rank]).max() < 1e-12
 
 
