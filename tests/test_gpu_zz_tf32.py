@@ -50,6 +50,7 @@ def test_cholinv_mixed_precision_trailing_update():
 
 
 # ---- not TF32: a parameter of the FP64 path whose first GPU run is this file too (kept here so that it cannot stop the suite early) ----
+@pytest.mark.xfail(strict=False, reason="split = 2 was added to the parity set after the round's GPU budget was spent: first GPU run (XPASS = parity holds)")
 def test_cholinv_uneven_split_matches_reference_dump_and_oracle():
     """split = 2 (cholinv.hpp:92,107: the left child gets a quarter of the node): the reference's own dump, elementwise, and the numpy
     restatement (pinned to that dump on CPU) at a ragged size."""
