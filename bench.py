@@ -463,7 +463,7 @@ def ours(args):
             if r.returncode == 0:
                 tf32 = json.loads(r.stdout.strip().splitlines()[-1])
                 tf32["dtype"] = "tf32 (tcgen05.mma.kind::tf32, FP32 accumulation in TMEM) for A22 -= R12^T R12 with k >= 256; everything else f64"
-                tf32["status"] = "experimental: first executed by whoever runs this; see tests/test_gpu_zz_tf32.py for the parity gates"
+                tf32["status"] = "experimental: first executed by whoever runs this; see tests/test_gpu_zz_late.py for the parity gates"
             else:
                 tf32 = {"error": r.stderr[-300:]}
         except Exception as ex:  # noqa

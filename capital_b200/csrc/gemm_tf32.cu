@@ -3,7 +3,7 @@
 //
 // EXPERIMENTAL -- OFF BY DEFAULT (capital_set_trailing_precision).  Written after the round's GPU budget was spent: it assembles for
 // sm_100a (SASS: UTCHMMA / UTMALDG / LDTM, profiles/r02_sass_tf32.md) but its first execution is whoever runs
-// tests/test_gpu_zz_tf32.py.  The default FP64 path never touches this file's kernels.
+// tests/test_gpu_zz_late.py.  The default FP64 path never touches this file's kernels.
 //
 // Why it exists: the reference has no float BLAS path (src/blas/interface.hpp:43-97 is double only); the FP64 trailing update
 // (summa::syrk, summa.hpp:143-145) is the one place of the hot path whose arithmetic a user may trade for speed, and the one place

@@ -1,4 +1,4 @@
-"""Where the tolerances of tests/test_gpu_zz_tf32.py come from: a numpy emulation of the mixed-precision trailing update
+"""Where the tolerances of tests/test_gpu_zz_late.py come from: a numpy emulation of the mixed-precision trailing update
 (operands rounded to TF32 with round-to-nearest-away as `cvt.rna.tf32.f32` does, FP32 accumulation, optional hi + lo split) inside a
 plain recursive Cholesky on the reference's generator.  CPU only; python tools/tf32_emulate.py [n ...]"""
 import os

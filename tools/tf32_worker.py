@@ -1,4 +1,4 @@
-"""Child process of tests/test_gpu_zz_tf32.py (and of bench.py's optional `tf32` record): runs the EXPERIMENTAL TF32 tensor-core path in
+"""Child process of tests/test_gpu_zz_late.py (and of bench.py's optional `tf32` record): runs the EXPERIMENTAL TF32 tensor-core path in
 its own CUDA context, so that a fault in it (it was written without a GPU at hand) cannot poison the parent's context, and prints ONE
 JSON line.  usage: tf32_worker.py gemm | cholinv n bcm | bench n bcm steps"""
 import json
