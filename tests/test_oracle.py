@@ -155,3 +155,21 @@ def test_cacqr_3d_restatement_matches_reference(name):
     assert np.abs(q - q_ref).max() < 1e-13
     assert np.abs(r - r_ref).max() < (1e-13 if ci else 1e-12) * np.abs(r_ref).max()
     assert co.qr_residual(a, q, r) < 1e-14 and co.qr_orthogonality(q) < 1e-15
+
+
+def test_tf32_gates_have_headroom_over_the_emulated_rounding():
+    """tests/test_gpu_zz_late.py gates the experimental TF32 trailing update against the FP64 results; the gates must sit well above what
+    a faithful implementation produces.  tools/tf32_emulate.py restates the kernel's arithmetic in numpy (cvt.rna.tf32 on the operands,
+    FP32 accumulation, optional hi + lo split)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("tf32_emulate", os.path.join(os.path.dirname(GOLD), "..", "tools", "tf32_emulate.py"))
+    em = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(em)
+    a = co.spd_global(512)
+    res = {p: co.cholesky_residual(a, em.cholesky(a, 64, p, 128)) for p in (0, 1, 3)}
+    assert res[0] < 1e-15 and 1e-13 < res[1] < 1e-7 and res[3] < 1e-9
+    rng = np.random.default_rng(1)
+    A, B = rng.standard_normal((1024, 96)), rng.standard_normal((1024, 160))
+    ref, den = A.T @ B, (np.abs(A).T @ np.abs(B)).max()
+    assert np.abs(em.product(A, B, 1) - ref).max() / den < 5e-4 / 4
+    assert np.abs(em.product(A, B, 3) - ref).max() / den < 2e-6 / 4
